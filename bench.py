@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- ESPNet inference throughput on B200 (BASELINE.json metric: ESPNet 512x512 crops/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+Workloads (BASELINE.json configs):
+  espnet_c_b64_fp32 (default, configs[1])  ESPNet-C encoder-only, batch 64 x 512x512, fp32, per GPU
+  espnet_b256_ens5  (configs[2])           full ESPNet, batch 256, 5-fold softmax ensemble
+  espnet_b64_fp32                          full ESPNet, batch 64, logits + arg-max
+A step = one pass of the hot path over one batch.  `value` is timed with the (normalised fp32) batch
+resident in HBM; `e2e` goes through the public u8 API with pinned HOST crops in and HOST masks out, the
+H2D / D2H copies inside the timed region.  One process per GPU (torchrun for N > 1), no collective in
+the data path (weak scaling: every rank has its own batch).
+
+--impl reference: the reference's CPU implementation of the same path.  The reference is pure Python on
+PyTorch and cannot travel to the GPU box, so this arm runs the oracle port (oracle/espnet_oracle.py,
+validated against the real reference through tests/golden) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0           # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal CUDA-core fp32 roof
+FLOP_PER_CROP_FULL = 3.636e9
+FLOP_PER_CROP_ENC = 3.636e9 - (154.7 + 18.0 + 21.5) * 1e6   # minus S8..S10 (decoder-only stages)
+
+
+def load_weights(fold, encoder_only):
+    path = os.path.join(ROOT, "tests", "golden", "weights_fold%d.npz" % fold)
+    if not os.path.isfile(path):
+        return None
+    z = np.load(path)
+    sd = {k: torch.from_numpy(z[k]) for k in z.files}
+    if encoder_only:
+        sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    return sd
+
+
+def synth_u8(B, H, W, seed):
+    """D1 of SURVEY.md 8(d): iid uniform BGR u8 crops (the hardest case for low-precision paths)."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (bounded sample)
+# ---------------------------------------------------------------------------------------------------
+def cpu_forward_fn(workload, sample):
+    from oracle import espnet_oracle as O       # checker / CPU baseline only -- never on the product path
+    enc = workload == "espnet_c_b64_fp32"
+    sd = load_weights(1, False)
+    if sd is None:
+        sd = O.random_state_dict(5, 2, 8, seed=0)
+    mean, std = O.FOLD_MEAN_STD[1]
+    u8 = synth_u8(sample, 512, 512, 1234)
+    esd = O.encoder_state_dict(sd)
+    sds = None
+    if workload == "espnet_b256_ens5":
+        sds = [load_weights(k, False) or O.random_state_dict(5, 2, 8, seed=k) for k in range(1, 6)]
+
+    def step():
+        if sds is not None:
+            return O.ensemble_mask(sds, u8, range(1, 6))[0]
+        x = torch.from_numpy(O.normalise_bgr_u8(u8, mean, std))
+        if enc:
+            return O.argmax_mask(O.upsample8_bilinear(O.espnet_encoder_forward(esd, x)))
+        return O.argmax_mask(O.espnet_forward(sd, x))
+    return step
+
+
+def time_cpu(workload, sample, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_forward_fn(workload, sample)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8 if args.workload != "espnet_b256_ens5" else 2
+    val, dt = time_cpu(args.workload, sample, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "ESPNet 512x512 crops/s", "value": val, "unit": "crops/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, sample),
+        "cpu_baseline": {"value": val, "unit": "crops/s", "cores": cores, "kind": "port",
+                         "sample": "%d synthetic 512x512 crops per step, oracle port of Model.py on torch %s CPU" % (sample, torch.__version__)},
+        "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(workload, batch):
+    names = {
+        "espnet_c_b64_fp32": "ESPNet-C encoder-only (classes=5,p=2,q=8), %d synthetic 512x512 BGR crops per GPU per step, fp32" % batch,
+        "espnet_b64_fp32": "full ESPNet (classes=5,p=2,q=8), %d synthetic 512x512 crops per GPU per step, fp32 logits + arg-max" % batch,
+        "espnet_b256_ens5": "full ESPNet (5,2,8), %d synthetic 512x512 crops per GPU per step, folds 1-5 softmax ensemble" % batch,
+    }
+    return {"workload": names[workload], "crop": "512x512", "batch_per_gpu": batch, "weights": "espnet_fold1 (tests/golden)",
+            "l2": "inputs (201 MB fp32 / 50 MB u8 per batch of 64) and activations (>2 GB) exceed the 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from glomeruli_segmentation_b200 import ESPNet, ESPNet_Encoder, ESPNetEnsemble, FOLD_MEAN_STD, _lib
+
+    wl = args.workload
+    B = args.batch or {"espnet_c_b64_fp32": 64, "espnet_b64_fp32": 64, "espnet_b256_ens5": 256}[wl]
+    H = W = 512
+    mean, std = FOLD_MEAN_STD[1]
+    if wl == "espnet_c_b64_fp32":
+        model = ESPNet_Encoder(5, 2, 8)
+        sd = load_weights(1, True)
+    else:
+        model = ESPNet(5, 2, 8)
+        sd = load_weights(1, False)
+    if sd is not None:
+        model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    ens = None
+    if wl == "espnet_b256_ens5":
+        models = [model]
+        for k in range(2, 6):
+            mk = ESPNet(5, 2, 8)
+            sdk = load_weights(k, False)
+            if sdk is not None:
+                mk.load_state_dict(sdk, strict=True)
+            models.append(mk.to(dev).eval())
+        ens = ESPNetEnsemble(models, [FOLD_MEAN_STD[k] for k in range(1, 6)])
+
+    u8_host = torch.from_numpy(synth_u8(B, H, W, 1234 + rank)).pin_memory()
+    mask_host = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+    u8_dev = u8_host.to(dev)
+    # device-resident normalised fp32 batch = what the reference's forward receives (P0 done once, outside the timing)
+    m_t = torch.tensor(mean, device=dev, dtype=torch.float32)
+    s_t = torch.tensor(std, device=dev, dtype=torch.float32)
+    x_dev = (((u8_dev.float() - m_t) / s_t) / 255.0).permute(0, 3, 1, 2).contiguous()
+    mask_dev = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+
+    if ens is not None:
+        def step_resident():
+            return ens.segment(u8_dev)
+    elif wl == "espnet_c_b64_fp32":
+        def step_resident():
+            return model(x_dev)
+    else:
+        logits = torch.empty((B, 5, H, W), dtype=torch.float32, device=dev)
+
+        def step_resident():
+            model._engine.forward(x_dev, _lib.IN_F32_NCHW, B, H, W, logits=logits, mask=mask_dev)
+            return logits
+
+    def step_e2e():
+        d = u8_host.to(dev, non_blocking=True)
+        if ens is not None:
+            mk = ens.segment(d)
+        else:
+            mk = model.segment(d, mean, std, out=mask_dev)
+        mask_host.copy_(mk, non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib().espnet_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = int(_lib.lib().espnet_launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # per-kernel share of the step (CUDA events on the launching stream, same inputs, separate pass)
+    prof_steps = min(args.steps, 5)
+    model.profile(True)
+    for _ in range(prof_steps):
+        step_resident()
+    torch.cuda.synchronize()
+    rep = model.profile_report()
+    model.profile(False)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    tot_ms = sum(v[0] for v in rep.values()) or 1.0
+    kernels = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps, "share": v[0] / tot_ms} for k, v in rep.items()}
+    top = max(rep, key=lambda k: rep[k][0]) if rep else None
+    roof = None
+    if top is not None:
+        per_launch_ms = rep[top][0] / rep[top][1]
+        # algorithmic bytes of one esp_branch launch at level 3: per crop it reads o1 (25 ch) and the
+        # residual (128 ch) and writes 128 ch of a 64x64 map, fp32
+        alg = {"esp_branch_l3": B * (25 + 128 + 128) * 64 * 64 * 4, "esp_branch_l2": B * (12 + 64 + 64) * 128 * 128 * 4}.get(top)
+        flops = {"esp_branch_l3": B * 4096 * 2 * 9 * 25 * 128, "esp_branch_l2": B * 16384 * 2 * 9 * 12 * 64}.get(top)
+        if alg is not None:
+            ach = alg / (per_launch_ms * 1e-3) / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_ms,
+                    "note": "fp32 mode: this kernel is CUDA-core FMA bound, not HBM bound (SURVEY.md 8(d)); see fp32_fma",
+                    "fp32_fma": {"achieved_tflops": flops / (per_launch_ms * 1e-3) / 1e12, "peak_tflops": FP32_FMA_PEAK_TFLOPS,
+                                 "frac": flops / (per_launch_ms * 1e-3) / 1e12 / FP32_FMA_PEAK_TFLOPS}}
+
+    cpu_sample = 4 if wl != "espnet_b256_ens5" else 1
+    cpu_val, cpu_dt = time_cpu(wl, cpu_sample, 3, 1) if world == 1 and not args.no_cpu else (None, None)
+    line = {
+        "metric": "ESPNet 512x512 crops/s", "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, B),
+        "mpx_per_s": value * H * W / 1e6,
+        "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(u8_host.numel()), "d2h_bytes_per_step": int(mask_host.numel()),
+                "ms_per_step": ms_e2e / args.steps, "api": "model.segment(u8 crops) -> u8 class map, pinned host buffers"},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "kernels": kernels,
+        "clocks": clocks,
+        "tflops_effective": value * (FLOP_PER_CROP_ENC if wl == "espnet_c_b64_fp32" else FLOP_PER_CROP_FULL) / 1e12,
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "crops/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "%d of the same synthetic 512x512 crops x 3 timed passes (%.1f s each), oracle port on torch %s CPU"
+                                          % (cpu_sample, cpu_dt, torch.__version__)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="espnet_c_b64_fp32", choices=["espnet_c_b64_fp32", "espnet_b64_fp32", "espnet_b256_ens5"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

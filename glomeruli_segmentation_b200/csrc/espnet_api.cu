@@ -1,0 +1,780 @@
+// libespnet_b200.so -- host side of the C ABI declared in include/espnet_b200.h:
+// weight packing (BN folding in fp64), workspace layout, stage scheduling and kernel launches.
+// No torch, no cuDNN, no CPU fallback: if a CUDA call fails the error is returned to the caller.
+#include "../../include/espnet_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels_fp32.cuh"
+#include "kernels_tc.cuh"
+#include "kernels_wsi.cuh"
+
+using namespace espnet;
+
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local std::string g_create_error;
+
+#define LAUNCH_COUNT() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+namespace {
+
+struct HostTensor {
+    const float* data;
+    std::vector<int64_t> shape;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto s : shape) n *= (size_t)s;
+        return n;
+    }
+};
+
+// offsets (in floats) of the packed, kernel-ready parameter arrays inside the device blob
+struct BlockW {
+    size_t c1 = 0, d1 = 0, chain = 0, s = 0, t = 0, a = 0;
+    size_t tc = 0;   // offset (bytes) into the fp16 blob for the tensor-core path
+};
+
+struct Packed {
+    size_t w1, l1_s, l1_t, l1_a, b1_s, b1_t, b1_a;
+    size_t b2_s, b2_t, b2_a, b3_s, b3_t, b3_a;
+    BlockW l2_0, l3_0;
+    std::vector<BlockW> l2, l3;
+    size_t cls_w;                        // encoder.classifier [256][NC]
+    size_t br_s, br_t, up3_w;            // br BN, up_l3 ConvT
+    size_t l3c_w;                        // level3_C [131][NC]
+    size_t c0_s, c0_t, c0_a;             // combine_l2_l3.0 BR (2NC)
+    size_t c1_w, c1_s, c1_t, c1_a;       // combine_l2_l3.1 CBR
+    size_t up2_w, u2_s, u2_t, u2_a;      // up_l2
+    size_t cv_w, cv_s, cv_t, cv_a;       // conv CBR
+    size_t clsT_w;                       // classifier ConvT
+};
+
+struct Workspace {
+    size_t inp1raw, out0cat, o1, l2a, l2b, out1cat, l3a, l3b, out2cat, enc, up3, t10, comb, total;
+};
+
+struct StageRef {
+    const float* ptr = nullptr;
+    size_t count = 0;
+};
+
+}  // namespace
+
+struct espnet_handle {
+    int classes = 0, p = 0, q = 0, net = 0, device = 0, mode = ESPNET_MODE_FP32;
+    int num_sms = 148;
+    std::string err;
+    bool packed = false;
+    float* dparams = nullptr;
+    size_t nparams = 0;
+    Packed pk;
+    std::map<std::string, StageRef> stages;
+    // per-kernel CUDA-event timing (espnet_set_profiling)
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    // host-convenience path (espnet_segment_host)
+    cudaStream_t own_stream = nullptr;
+    void* hb_in = nullptr; void* hb_mask = nullptr; void* hb_ws = nullptr;
+    size_t hb_in_sz = 0, hb_mask_sz = 0, hb_ws_sz = 0;
+};
+
+namespace {
+
+int fail(espnet_t* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail((h), ESPNET_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Brackets one kernel launch with CUDA events on the launching stream when profiling is on.
+struct ProfScope {
+    espnet_t* h; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; const char* name;
+    ProfScope(espnet_t* h_, const char* name_, cudaStream_t st_) : h(h_), st(st_), name(name_) {
+        if (!h->profiling) return;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+    }
+    ~ProfScope() {
+        if (!e0) return;
+        cudaEventRecord(e1, st);
+        h->prof.push_back({name, e0, e1});
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// packing
+// ----------------------------------------------------------------------------------------------
+struct Packer {
+    std::vector<float> blob;
+    const std::map<std::string, HostTensor>* sd = nullptr;
+    std::string missing;
+
+    size_t add(const std::vector<float>& v) {
+        while (blob.size() % 4) blob.push_back(0.f);      // 16 B alignment for float4 / LDS.128 rows
+        const size_t off = blob.size();
+        blob.insert(blob.end(), v.begin(), v.end());
+        return off;
+    }
+    const HostTensor* get(const std::string& name, std::initializer_list<int64_t> shape) {
+        auto it = sd->find(name);
+        if (it == sd->end()) { if (missing.empty()) missing = "missing tensor '" + name + "'"; return nullptr; }
+        if (it->second.shape != std::vector<int64_t>(shape)) {
+            if (missing.empty()) missing = "tensor '" + name + "' has the wrong shape";
+            return nullptr;
+        }
+        return &it->second;
+    }
+    // eval-mode BN (eps 1e-3) folded to y = x*s + t, in fp64 (running_var holds denormals)
+    bool bn(const std::string& key, int c, size_t& s_off, size_t& t_off) {
+        const HostTensor *g = get(key + ".weight", {c}), *b = get(key + ".bias", {c});
+        const HostTensor *m = get(key + ".running_mean", {c}), *v = get(key + ".running_var", {c});
+        if (!g || !b || !m || !v) return false;
+        std::vector<float> s(c), t(c);
+        for (int i = 0; i < c; ++i) {
+            const double sc = (double)g->data[i] / std::sqrt((double)v->data[i] + 1e-3);
+            s[i] = (float)sc;
+            t[i] = (float)((double)b->data[i] - (double)m->data[i] * sc);
+        }
+        s_off = add(s);
+        t_off = add(t);
+        return true;
+    }
+    bool vec(const std::string& name, int c, size_t& off) {
+        const HostTensor* a = get(name, {c});
+        if (!a) return false;
+        off = add(std::vector<float>(a->data, a->data + c));
+        return true;
+    }
+    // conv weight [co][ci][k][k] -> [tap][ci][pad4(co)]
+    bool conv_tap_ci_co(const std::string& name, int co, int ci, int k, size_t& off) {
+        const HostTensor* w = get(name, {co, ci, k, k});
+        if (!w) return false;
+        const int cp = pad4(co), taps = k * k;
+        std::vector<float> v((size_t)taps * ci * cp, 0.f);
+        for (int o = 0; o < co; ++o)
+            for (int c = 0; c < ci; ++c)
+                for (int t = 0; t < taps; ++t) v[((size_t)t * ci + c) * cp + o] = w->data[((size_t)o * ci + c) * taps + t];
+        off = add(v);
+        return true;
+    }
+    // conv weight [co][ci][k][k] -> [ci][tap][co] (unpadded; decoder kernels)
+    bool conv_ci_tap_co(const std::string& name, int co, int ci, int k, size_t& off) {
+        const HostTensor* w = get(name, {co, ci, k, k});
+        if (!w) return false;
+        const int taps = k * k;
+        std::vector<float> v((size_t)taps * ci * co, 0.f);
+        for (int o = 0; o < co; ++o)
+            for (int c = 0; c < ci; ++c)
+                for (int t = 0; t < taps; ++t) v[((size_t)c * taps + t) * co + o] = w->data[((size_t)o * ci + c) * taps + t];
+        off = add(v);
+        return true;
+    }
+    bool raw(const std::string& name, std::initializer_list<int64_t> shape, size_t& off) {
+        const HostTensor* w = get(name, shape);
+        if (!w) return false;
+        off = add(std::vector<float>(w->data, w->data + w->numel()));
+        return true;
+    }
+    // one DownSamplerB / ESP block: c1 (k = 3 or 1), d1, chain, BN + PReLU
+    bool block(const std::string& key, int cin, int cout, bool down, BlockW& bw) {
+        const int n = cout / 5, n1 = cout - 4 * n;
+        bool ok = conv_tap_ci_co(key + ".c1.conv.weight", n, cin, down ? 3 : 1, bw.c1);
+        ok = ok && conv_tap_ci_co(key + ".d1.conv.weight", n1, n, 3, bw.d1);
+        // chain: [4][9][n][pad4(n)]
+        const int cp = pad4(n);
+        std::vector<float> v((size_t)4 * 9 * n * cp, 0.f);
+        const int ds[4] = {2, 4, 8, 16};
+        for (int b = 0; b < 4 && ok; ++b) {
+            const HostTensor* w = get(key + ".d" + std::to_string(ds[b]) + ".conv.weight", {n, n, 3, 3});
+            if (!w) { ok = false; break; }
+            for (int o = 0; o < n; ++o)
+                for (int c = 0; c < n; ++c)
+                    for (int t = 0; t < 9; ++t) v[(((size_t)b * 9 + t) * n + c) * cp + o] = w->data[((size_t)o * n + c) * 9 + t];
+        }
+        if (!ok) return false;
+        bw.chain = add(v);
+        const std::string bnk = down ? key + ".bn" : key + ".bn.bn";
+        const std::string ak = down ? key + ".act.weight" : key + ".bn.act.weight";
+        return bn(bnk, cout, bw.s, bw.t) && vec(ak, cout, bw.a);
+    }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Workspace layout(const espnet_t* h, int B, int H, int W) {
+    Workspace w{};
+    const size_t P2 = (size_t)(H / 2) * (W / 2), P4 = (size_t)(H / 4) * (W / 4), P8 = (size_t)(H / 8) * (W / 8);
+    const size_t NC = (size_t)h->classes;
+    size_t off = 0;
+    auto take = [&](size_t elems) { const size_t o = off; off = align_up(off + elems, 64); return o; };
+    w.inp1raw = take((size_t)B * 3 * P2);
+    w.out0cat = take((size_t)B * 19 * P2);
+    w.o1 = take((size_t)B * 12 * P4 > (size_t)B * 25 * P8 ? (size_t)B * 12 * P4 : (size_t)B * 25 * P8);
+    w.l2a = take((size_t)B * 64 * P4);
+    w.l2b = take((size_t)B * 64 * P4);
+    w.out1cat = take((size_t)B * 131 * P4);
+    w.l3a = take((size_t)B * 128 * P8);
+    w.l3b = take((size_t)B * 128 * P8);
+    w.out2cat = take((size_t)B * 256 * P8);
+    w.enc = take((size_t)B * NC * P8);
+    w.up3 = take((size_t)B * NC * P4);
+    w.t10 = take((size_t)B * 2 * NC * P4);
+    w.comb = take((size_t)B * NC * P2);
+    w.total = off;
+    return w;
+}
+
+template <typename K>
+int set_smem(espnet_t* h, K kernel, size_t bytes) {
+    CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return ESPNET_OK;
+}
+
+int grid_for(const espnet_t* h, long long items) {
+    long long g = items < (long long)h->num_sms ? items : (long long)h->num_sms;
+    return (int)(g < 1 ? 1 : g);
+}
+
+long long tile_items(int B, int H, int W) { return (long long)B * ((H + kRows - 1) / kRows) * ((W + 31) / 32); }
+
+template <int CIN, int CO>
+int run_reduce1x1(espnet_t* h, const float* in, size_t w_off, float* o1, int B, int HW, cudaStream_t st) {
+    const size_t smem = (size_t)CIN * pad4(CO) * sizeof(float);
+    const long long items = (long long)B * ((HW + 127) / 128);
+    const int threads = 256;
+    long long ctas = (items + 7) / 8;
+    const long long cap = 2LL * h->num_sms;
+    if (ctas > cap) ctas = cap;
+    { ProfScope _ps(h, CIN == 64 ? "reduce1x1_l2" : "reduce1x1_l3", st); reduce1x1_kernel<CIN, CO><<<(int)ctas, threads, smem, st>>>(in, h->dparams + w_off, o1, B, HW); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+template <int CIN, int CO>
+int run_reduce3x3(espnet_t* h, const float* in, size_t w_off, float* o1, int B, int Hi, int Wi, cudaStream_t st) {
+    const size_t smem = (size_t)9 * CIN * pad4(CO) * sizeof(float);
+    int rc = set_smem(h, reduce3x3s2_kernel<CIN, CO>, smem);
+    if (rc) return rc;
+    const int grid = grid_for(h, tile_items(B, Hi / 2, Wi / 2));
+    { ProfScope _ps(h, CIN == 19 ? "reduce3x3s2_l2" : "reduce3x3s2_l3", st); reduce3x3s2_kernel<CIN, CO><<<grid, 384, smem, st>>>(in, h->dparams + w_off, o1, B, Hi, Wi); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+template <int N, int CO1, int CO>
+int run_branch(espnet_t* h, const BlockW& bw, const float* o1, const float* res, float* out, float* out2, int C2, int c2_off,
+               size_t s2, size_t t2, size_t a2, int B, int H, int W, cudaStream_t st) {
+    constexpr int C = CO1 + 4 * CO;
+    const size_t smem = ((size_t)9 * N * pad4(CO1) + (size_t)36 * N * pad4(CO) + 6 * C) * sizeof(float);
+    int rc = set_smem(h, esp_branch_kernel<N, CO1, CO>, smem);
+    if (rc) return rc;
+    BranchParams p{};
+    p.o1 = o1;
+    p.w_d1 = h->dparams + bw.d1;
+    p.w_chain = h->dparams + bw.chain;
+    p.res = res;
+    p.s = h->dparams + bw.s; p.t = h->dparams + bw.t; p.a = h->dparams + bw.a;
+    p.out = out;
+    p.s2 = h->dparams + s2; p.t2 = h->dparams + t2; p.a2 = h->dparams + a2;
+    p.out2 = out2; p.C2 = C2; p.c2_off = c2_off;
+    p.B = B; p.H = H; p.W = W;
+    const int grid = grid_for(h, tile_items(B, H, W));
+    { ProfScope _ps(h, N == 12 ? "esp_branch_l2" : "esp_branch_l3", st); esp_branch_kernel<N, CO1, CO><<<grid, 384, smem, st>>>(p); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+template <int NC>
+int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, float* ws, cudaStream_t st) {
+    const int B = a->B, H = a->H, W = a->W;
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+    const Packed& pk = h->pk;
+    const float* P = h->dparams;
+    const bool full = h->net == ESPNET_NET_FULL;
+    {
+        Head3Params<NC> p{};
+        p.in = ws + L.out2cat;
+        p.w = P + pk.cls_w;
+        p.B = B; p.H8 = H8; p.W8 = W8;
+        if (full) {
+            p.bn_s = P + pk.br_s; p.bn_t = P + pk.br_t; p.wt = P + pk.up3_w;
+            p.up_out = ws + L.up3;
+            p.enc_out = nullptr;
+        } else {
+            p.enc_out = a->logits ? a->logits : ws + L.enc;
+        }
+        const size_t n = (size_t)B * H8 * W8;
+        int grid = (int)((n + 255) / 256);
+        if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
+        { ProfScope _ps(h, "head3", st); head3_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        if (!full) {
+            h->stages["encoder.classifier"] = {p.enc_out, (size_t)B * NC * H8 * W8};
+            if (a->mask) {
+                dim3 g((W + 31) / 32, (H + 7) / 8, B);
+                { ProfScope _ps(h, "upsample8_argmax", st); upsample8_argmax_kernel<NC><<<g, 256, 0, st>>>(p.enc_out, B, H8, W8, a->mask, nullptr); }
+                LAUNCH_COUNT();
+                CUDA_TRY(h, cudaPeekAtLastError());
+            }
+            return ESPNET_OK;
+        }
+        h->stages["up_l3"] = {ws + L.up3, (size_t)B * NC * H4 * W4};
+    }
+    {
+        DecAParams<NC> p{};
+        p.out1cat = ws + L.out1cat; p.up3 = ws + L.up3; p.w = P + pk.l3c_w;
+        p.s = P + pk.c0_s; p.t = P + pk.c0_t; p.a = P + pk.c0_a;
+        p.tout = ws + L.t10; p.B = B; p.H4 = H4; p.W4 = W4;
+        const size_t n = (size_t)B * H4 * W4;
+        int grid = (int)((n + 255) / 256);
+        if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
+        { ProfScope _ps(h, "dec_a", st); dec_a_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        h->stages["combine_l2_l3.0"] = {ws + L.t10, (size_t)B * 2 * NC * H4 * W4};
+    }
+    {
+        DecBParams<NC> p{};
+        p.tin = ws + L.t10; p.w = P + pk.c1_w;
+        p.s = P + pk.c1_s; p.t = P + pk.c1_t; p.a = P + pk.c1_a;
+        p.wt = P + pk.up2_w;
+        p.s2 = P + pk.u2_s; p.t2 = P + pk.u2_t; p.a2 = P + pk.u2_a;
+        p.comb = ws + L.comb; p.B = B; p.H4 = H4; p.W4 = W4;
+        const size_t n = (size_t)B * H4 * W4;
+        int grid = (int)((n + 255) / 256);
+        if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
+        { ProfScope _ps(h, "dec_b", st); dec_b_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        h->stages["up_l2"] = {ws + L.comb, (size_t)B * NC * H2 * W2};
+    }
+    {
+        DecCParams<NC> p{};
+        p.comb = ws + L.comb; p.out0cat = ws + L.out0cat; p.w = P + pk.cv_w;
+        p.s = P + pk.cv_s; p.t = P + pk.cv_t; p.a = P + pk.cv_a;
+        p.wt = P + pk.clsT_w;
+        p.logits = a->logits; p.mask = a->mask; p.prob_acc = a->prob_acc;
+        p.prob_init = a->prob_init; p.mask_from_prob = a->mask_from_prob;
+        p.B = B; p.H2 = H2; p.W2 = W2;
+        dim3 g((W2 + 31) / 32, (H2 + 7) / 8, B);
+        { ProfScope _ps(h, "dec_c", st); dec_c_kernel<NC><<<g, 256, 0, st>>>(p); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+    }
+    return ESPNET_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int espnet_version(void) { return 100; }
+unsigned long long espnet_launch_count(void) { return g_launches.load(); }
+
+const char* espnet_last_error(const espnet_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int espnet_create(int classes, int p, int q, int net, int device, espnet_t** out) {
+    if (!out) return fail(nullptr, ESPNET_EINVAL, "espnet_create: out is NULL");
+    *out = nullptr;
+    if (classes != 5 && classes != 20)
+        return fail(nullptr, ESPNET_ESHAPE, "espnet_create: classes must be 5 or 20 (kernels are instantiated for those)");
+    if (p < 1 || q < 1) return fail(nullptr, ESPNET_EINVAL, "espnet_create: p and q must be >= 1 (the reference forward needs one block per level)");
+    if (net != ESPNET_NET_FULL && net != ESPNET_NET_ENCODER) return fail(nullptr, ESPNET_EINVAL, "espnet_create: bad net");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ESPNET_ECUDA, std::string("espnet_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, ESPNET_EINVAL, "espnet_create: bad device index");
+    cudaDeviceProp prop{};
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, ESPNET_ECUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, ESPNET_ECUDA, "espnet_create: this library holds sm_100a code only (B200); device is sm_" +
+                                               std::to_string(prop.major) + std::to_string(prop.minor));
+    espnet_t* h = new espnet_t();
+    h->classes = classes; h->p = p; h->q = q; h->net = net; h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    {
+        DeviceGuard g(device);
+        e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete h; return fail(nullptr, ESPNET_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    }
+    *out = h;
+    return ESPNET_OK;
+}
+
+void espnet_destroy(espnet_t* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    if (h->dparams) cudaFree(h->dparams);
+    if (h->hb_in) cudaFree(h->hb_in);
+    if (h->hb_mask) cudaFree(h->hb_mask);
+    if (h->hb_ws) cudaFree(h->hb_ws);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    delete h;
+}
+
+int espnet_set_mode(espnet_t* h, int mode) {
+    if (!h) return ESPNET_EINVAL;
+    if (mode != ESPNET_MODE_FP32 && mode != ESPNET_MODE_F16TC) return fail(h, ESPNET_EINVAL, "espnet_set_mode: unknown mode");
+    if (mode == ESPNET_MODE_F16TC && !tc_path_available())
+        return fail(h, ESPNET_ESTATE, "espnet_set_mode: the tcgen05 fp16 path is not built into this library yet");
+    h->mode = mode;
+    return ESPNET_OK;
+}
+
+int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n) {
+    if (!h || !tensors || n <= 0) return fail(h, ESPNET_EINVAL, "espnet_pack_weights: bad arguments");
+    std::map<std::string, HostTensor> sd;
+    for (int i = 0; i < n; ++i) {
+        if (!tensors[i].name || !tensors[i].data || tensors[i].ndim < 0 || tensors[i].ndim > 4)
+            return fail(h, ESPNET_EINVAL, "espnet_pack_weights: malformed tensor descriptor");
+        HostTensor t;
+        t.data = tensors[i].data;
+        t.shape.assign(tensors[i].shape, tensors[i].shape + tensors[i].ndim);
+        sd[tensors[i].name] = t;
+    }
+    const int NC = h->classes;
+    const std::string e = h->net == ESPNET_NET_FULL ? "encoder." : "";
+    Packer pk;
+    pk.sd = &sd;
+    Packed& o = h->pk;
+    o.l2.assign(h->p, BlockW());
+    o.l3.assign(h->q, BlockW());
+    bool ok = true;
+    {   // level1: [16][3][3][3] -> [(ci*9+tap)][16]
+        const HostTensor* w = pk.get(e + "level1.conv.weight", {16, 3, 3, 3});
+        if (w) {
+            std::vector<float> v(27 * 16);
+            for (int co = 0; co < 16; ++co)
+                for (int k = 0; k < 27; ++k) v[k * 16 + co] = w->data[co * 27 + k];
+            o.w1 = pk.add(v);
+        } else ok = false;
+    }
+    ok = ok && pk.bn(e + "level1.bn", 16, o.l1_s, o.l1_t) && pk.vec(e + "level1.act.weight", 16, o.l1_a);
+    ok = ok && pk.bn(e + "b1.bn", 19, o.b1_s, o.b1_t) && pk.vec(e + "b1.act.weight", 19, o.b1_a);
+    ok = ok && pk.bn(e + "b2.bn", 131, o.b2_s, o.b2_t) && pk.vec(e + "b2.act.weight", 131, o.b2_a);
+    ok = ok && pk.bn(e + "b3.bn", 256, o.b3_s, o.b3_t) && pk.vec(e + "b3.act.weight", 256, o.b3_a);
+    ok = ok && pk.block(e + "level2_0", 19, 64, true, o.l2_0);
+    for (int i = 0; i < h->p && ok; ++i) ok = pk.block(e + "level2." + std::to_string(i), 64, 64, false, o.l2[i]);
+    ok = ok && pk.block(e + "level3_0", 131, 128, true, o.l3_0);
+    for (int i = 0; i < h->q && ok; ++i) ok = pk.block(e + "level3." + std::to_string(i), 128, 128, false, o.l3[i]);
+    ok = ok && pk.conv_ci_tap_co(e + "classifier.conv.weight", NC, 256, 1, o.cls_w);
+    if (ok && h->net == ESPNET_NET_FULL) {
+        ok = ok && pk.bn("br", NC, o.br_s, o.br_t);
+        ok = ok && pk.raw("up_l3.0.weight", {NC, NC, 2, 2}, o.up3_w);
+        ok = ok && pk.conv_ci_tap_co("level3_C.conv.weight", NC, 131, 1, o.l3c_w);
+        ok = ok && pk.bn("combine_l2_l3.0.bn", 2 * NC, o.c0_s, o.c0_t) && pk.vec("combine_l2_l3.0.act.weight", 2 * NC, o.c0_a);
+        ok = ok && pk.conv_ci_tap_co("combine_l2_l3.1.conv.weight", NC, 2 * NC, 3, o.c1_w);
+        ok = ok && pk.bn("combine_l2_l3.1.bn", NC, o.c1_s, o.c1_t) && pk.vec("combine_l2_l3.1.act.weight", NC, o.c1_a);
+        ok = ok && pk.raw("up_l2.0.weight", {NC, NC, 2, 2}, o.up2_w);
+        ok = ok && pk.bn("up_l2.1.bn", NC, o.u2_s, o.u2_t) && pk.vec("up_l2.1.act.weight", NC, o.u2_a);
+        ok = ok && pk.conv_ci_tap_co("conv.conv.weight", NC, NC + 19, 3, o.cv_w);
+        ok = ok && pk.bn("conv.bn", NC, o.cv_s, o.cv_t) && pk.vec("conv.act.weight", NC, o.cv_a);
+        ok = ok && pk.raw("classifier.weight", {NC, NC, 2, 2}, o.clsT_w);
+    }
+    if (!ok) return fail(h, ESPNET_EMISSING, "espnet_pack_weights: " + (pk.missing.empty() ? std::string("packing failed") : pk.missing));
+    DeviceGuard g(h->device);
+    if (h->dparams && h->nparams < pk.blob.size()) { cudaFree(h->dparams); h->dparams = nullptr; }
+    if (!h->dparams) CUDA_TRY(h, cudaMalloc(&h->dparams, pk.blob.size() * sizeof(float)));
+    h->nparams = pk.blob.size();
+    // synchronous copy: the host buffers belong to the caller and may go away after we return
+    CUDA_TRY(h, cudaMemcpy(h->dparams, pk.blob.data(), pk.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->packed = true;
+    return ESPNET_OK;
+}
+
+size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W) {
+    if (!h || B <= 0 || H <= 0 || W <= 0) return 0;
+    return layout(h, B, H, W).total * sizeof(float);
+}
+
+int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
+    if (!h || !a) return fail(h, ESPNET_EINVAL, "espnet_forward: NULL argument");
+    if (!h->packed) return fail(h, ESPNET_ESTATE, "espnet_forward: weights have not been packed (espnet_pack_weights)");
+    if (!a->x || !a->workspace) return fail(h, ESPNET_EINVAL, "espnet_forward: x / workspace is NULL");
+    if (a->B <= 0 || a->H <= 0 || a->W <= 0) return fail(h, ESPNET_ESHAPE, "espnet_forward: empty batch or crop");
+    if (a->B > 65535) return fail(h, ESPNET_ESHAPE, "espnet_forward: B > 65535, split the batch");
+    if ((a->H % 8) || (a->W % 8))
+        return fail(h, ESPNET_ESHAPE, "espnet_forward: H and W must be multiples of 8 (the reference's concat needs it)");
+    if (a->in_fmt < 0 || a->in_fmt > 2) return fail(h, ESPNET_EINVAL, "espnet_forward: unknown in_fmt");
+    if (a->in_fmt == ESPNET_IN_U8_SLIDE && (!a->origins || a->slide_h <= 0 || a->slide_w <= 0))
+        return fail(h, ESPNET_EINVAL, "espnet_forward: slide input needs origins and slide size");
+    if (h->net == ESPNET_NET_ENCODER && a->prob_acc) return fail(h, ESPNET_EINVAL, "espnet_forward: prob_acc needs the full net");
+    const Workspace L = layout(h, a->B, a->H, a->W);
+    if (a->workspace_bytes < L.total * sizeof(float)) return fail(h, ESPNET_ESTATE, "espnet_forward: workspace too small");
+    if ((size_t)a->H * a->W > ((size_t)1 << 30)) return fail(h, ESPNET_ESHAPE, "espnet_forward: crop too large for 32-bit plane offsets");
+
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)a->stream;
+    float* ws = (float*)a->workspace;
+    const float* P = h->dparams;
+    const Packed& pk = h->pk;
+    const int B = a->B, H = a->H, W = a->W;
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+    h->stages.clear();
+
+    if (h->mode == ESPNET_MODE_F16TC) return fail(h, ESPNET_ESTATE, "espnet_forward: tcgen05 path not available in this build");
+
+    // ---- S1 stem -----------------------------------------------------------------------------------
+    {
+        StemParams p{};
+        p.x = a->x; p.in_fmt = a->in_fmt; p.B = B; p.H = H; p.W = W;
+        for (int c = 0; c < 3; ++c) { p.mean[c] = a->mean[c]; p.stdv[c] = a->std_[c]; }
+        p.origins = a->origins; p.slide_h = a->slide_h; p.slide_w = a->slide_w;
+        p.w1 = P + pk.w1;
+        p.l1_s = P + pk.l1_s; p.l1_t = P + pk.l1_t; p.l1_a = P + pk.l1_a;
+        p.b1_s = P + pk.b1_s; p.b1_t = P + pk.b1_t; p.b1_a = P + pk.b1_a;
+        p.out0cat = ws + L.out0cat; p.inp1raw = ws + L.inp1raw;
+        dim3 grid((W2 + 31) / 32, (H2 + 7) / 8, B);
+        {
+            ProfScope _ps(h, "stem", st);
+            if (a->in_fmt == 0) stem_kernel<0><<<grid, 256, 0, st>>>(p);
+            else if (a->in_fmt == 1) stem_kernel<1><<<grid, 256, 0, st>>>(p);
+            else stem_kernel<2><<<grid, 256, 0, st>>>(p);
+        }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        const size_t n = (size_t)B * 3 * H4 * W4;
+        int g2 = (int)((n + 255) / 256);
+        if (g2 > 8 * h->num_sms) g2 = 8 * h->num_sms;
+        { ProfScope _ps(h, "pool_b2", st); pool_b2_kernel<<<g2, 256, 0, st>>>(ws + L.inp1raw, B, H2, W2, P + pk.b2_s, P + pk.b2_t, P + pk.b2_a, ws + L.out1cat, 131, 128); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        h->stages["b1"] = {ws + L.out0cat, (size_t)B * 19 * H2 * W2};
+    }
+    int rc;
+    // ---- S2/S3 level 2 -----------------------------------------------------------------------------
+    rc = run_reduce3x3<19, 12>(h, ws + L.out0cat, pk.l2_0.c1, ws + L.o1, B, H2, W2, st);
+    if (rc) return rc;
+    rc = run_branch<12, 16, 12>(h, pk.l2_0, ws + L.o1, nullptr, ws + L.l2a, ws + L.out1cat, 131, 64, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
+    if (rc) return rc;
+    {
+        float* cur = ws + L.l2a;
+        float* nxt = ws + L.l2b;
+        for (int i = 0; i < h->p; ++i) {
+            const bool last = i == h->p - 1;
+            rc = run_reduce1x1<64, 12>(h, cur, pk.l2[i].c1, ws + L.o1, B, H4 * W4, st);
+            if (rc) return rc;
+            rc = run_branch<12, 16, 12>(h, pk.l2[i], ws + L.o1, cur, last ? nullptr : nxt, last ? ws + L.out1cat : nullptr, 131, 0,
+                                        pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
+            if (rc) return rc;
+            float* t = cur; cur = nxt; nxt = t;
+        }
+        h->stages["b2"] = {ws + L.out1cat, (size_t)B * 131 * H4 * W4};
+    }
+    // ---- S5/S6 level 3 -----------------------------------------------------------------------------
+    rc = run_reduce3x3<131, 25>(h, ws + L.out1cat, pk.l3_0.c1, ws + L.o1, B, H4, W4, st);
+    if (rc) return rc;
+    rc = run_branch<25, 28, 25>(h, pk.l3_0, ws + L.o1, nullptr, ws + L.l3a, ws + L.out2cat, 256, 0, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
+    if (rc) return rc;
+    {
+        float* cur = ws + L.l3a;
+        float* nxt = ws + L.l3b;
+        for (int i = 0; i < h->q; ++i) {
+            const bool last = i == h->q - 1;
+            rc = run_reduce1x1<128, 25>(h, cur, pk.l3[i].c1, ws + L.o1, B, H8 * W8, st);
+            if (rc) return rc;
+            rc = run_branch<25, 28, 25>(h, pk.l3[i], ws + L.o1, cur, last ? nullptr : nxt, last ? ws + L.out2cat : nullptr, 256, 128,
+                                        pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
+            if (rc) return rc;
+            float* t = cur; cur = nxt; nxt = t;
+        }
+        h->stages["b3"] = {ws + L.out2cat, (size_t)B * 256 * H8 * W8};
+    }
+    // ---- S7..S10 heads / decoder -------------------------------------------------------------------
+    if (h->classes == 5) return run_tail<5>(h, a, L, ws, st);
+    return run_tail<20>(h, a, L, ws, st);
+}
+
+int espnet_set_profiling(espnet_t* h, int on) {
+    if (!h) return ESPNET_EINVAL;
+    DeviceGuard g(h->device);
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    h->prof.clear();
+    h->profiling = on != 0;
+    return ESPNET_OK;
+}
+
+int espnet_get_profile(espnet_t* h, char* names, float* total_ms, int* launches, int max_entries, int* n_entries) {
+    if (!h || !names || !total_ms || !launches || !n_entries || max_entries <= 0) return fail(h, ESPNET_EINVAL, "espnet_get_profile: bad arguments");
+    DeviceGuard g(h->device);
+    std::vector<std::string> order;
+    std::map<std::string, std::pair<double, int>> agg;
+    for (auto& r : h->prof) {
+        CUDA_TRY(h, cudaEventSynchronize(r.e1));
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, r.e0, r.e1));
+        if (!agg.count(r.name)) order.push_back(r.name);
+        agg[r.name].first += ms;
+        agg[r.name].second += 1;
+    }
+    int n = 0;
+    for (auto& k : order) {
+        if (n >= max_entries) break;
+        std::snprintf(names + 64 * n, 64, "%s", k.c_str());
+        total_ms[n] = (float)agg[k].first;
+        launches[n] = agg[k].second;
+        ++n;
+    }
+    *n_entries = n;
+    return ESPNET_OK;
+}
+
+int espnet_read_stage(espnet_t* h, const char* stage, float* dst, size_t dst_elems, size_t* count, void* stream) {
+    if (!h || !stage) return fail(h, ESPNET_EINVAL, "espnet_read_stage: NULL argument");
+    auto it = h->stages.find(stage);
+    if (it == h->stages.end()) return fail(h, ESPNET_EINVAL, std::string("espnet_read_stage: unknown stage '") + stage + "'");
+    if (count) *count = it->second.count;
+    if (!dst) return ESPNET_OK;
+    if (dst_elems < it->second.count) return fail(h, ESPNET_ESTATE, "espnet_read_stage: destination too small");
+    DeviceGuard g(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(dst, it->second.ptr, it->second.count * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ESPNET_OK;
+}
+
+int espnet_segment_host(espnet_t* h, const uint8_t* crops_host, int B, int H, int W, const float mean[3], const float std_[3],
+                        uint8_t* masks_host) {
+    if (!h || !crops_host || !masks_host || !mean || !std_) return fail(h, ESPNET_EINVAL, "espnet_segment_host: NULL argument");
+    if (B <= 0 || H <= 0 || W <= 0 || (H % 8) || (W % 8)) return fail(h, ESPNET_ESHAPE, "espnet_segment_host: bad shape");
+    DeviceGuard g(h->device);
+    const size_t in_sz = (size_t)B * H * W * 3, mask_sz = (size_t)B * H * W, ws_sz = espnet_workspace_bytes(h, B, H, W);
+    auto grow = [&](void*& ptr, size_t& have, size_t need) -> cudaError_t {
+        if (have >= need) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; have = 0;
+        cudaError_t e = cudaMalloc(&ptr, need);
+        if (e == cudaSuccess) have = need;
+        return e;
+    };
+    CUDA_TRY(h, grow(h->hb_in, h->hb_in_sz, in_sz));
+    CUDA_TRY(h, grow(h->hb_mask, h->hb_mask_sz, mask_sz));
+    CUDA_TRY(h, grow(h->hb_ws, h->hb_ws_sz, ws_sz));
+    CUDA_TRY(h, cudaMemcpyAsync(h->hb_in, crops_host, in_sz, cudaMemcpyHostToDevice, h->own_stream));
+    espnet_forward_args a{};
+    a.x = h->hb_in; a.in_fmt = ESPNET_IN_U8_BGR_HWC; a.B = B; a.H = H; a.W = W;
+    for (int c = 0; c < 3; ++c) { a.mean[c] = mean[c]; a.std_[c] = std_[c]; }
+    a.mask = (uint8_t*)h->hb_mask;
+    a.workspace = h->hb_ws; a.workspace_bytes = h->hb_ws_sz; a.stream = h->own_stream;
+    int rc = espnet_forward(h, &a);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(masks_host, h->hb_mask, mask_sz, cudaMemcpyDeviceToHost, h->own_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->own_stream));
+    return ESPNET_OK;
+}
+
+// ---------------------------------------------------------------------------------- stitching
+int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit, const int32_t* boxes,
+                        const int64_t* mask_offsets, const uint8_t* masks, int n_boxes, void* stream) {
+    if (!slide_mask || !boxes || !mask_offsets || !masks || slide_h <= 0 || slide_w <= 0 || n_boxes < 0) return ESPNET_EINVAL;
+    if (((uintptr_t)slide_mask & 3) != 0) return ESPNET_EINVAL;   // 32-bit merge words
+    if (n_boxes == 0) return ESPNET_OK;
+    dim3 grid(n_boxes, 32);
+    stitch_boxes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(slide_mask, slide_h, slide_w, y_limit, boxes,
+                                                               (const long long*)mask_offsets, masks, n_boxes);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks, int n_x, int n_y,
+                       int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream) {
+    if (!slide_mask || !tile_masks || slide_h <= 0 || slide_w <= 0 || n_x <= 0 || n_y <= 0 || win_x <= 0 || win_y <= 0 ||
+        stride_x <= 0 || stride_y <= 0 || tile_row0 < 0 || tile_rows < 0 || tile_row0 + tile_rows > n_y)
+        return ESPNET_EINVAL;
+    if (tile_rows == 0) return ESPNET_OK;
+    const long long ylo = (long long)tile_row0 * stride_y;
+    long long yhi = (long long)(tile_row0 + tile_rows - 1) * stride_y + win_y;
+    if (yhi > slide_h) yhi = slide_h;
+    if (yhi > y_limit) yhi = y_limit;
+    if (yhi <= ylo) return ESPNET_OK;
+    int gx = (slide_w + 255) / 256;
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, (unsigned)(yhi - ylo));
+    if (grid.y > 65535) return ESPNET_ESHAPE;
+    stitch_grid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(slide_mask, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x, win_y,
+                                                              stride_x, stride_y, tile_row0, tile_rows);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+// Source index LUT of the reference's per-window /8 nearest resize + paste along one axis
+// (eval_wsi_segmentation.py:180-195, 225-240): windows [k*ws, min((k+1)*ws, len)), each resized to
+// int(w/8) samples with cv2's INTER_NEAREST rule sx = min(floor(dx * (w / int(w/8))), w-1) and pasted
+// at [xmin//8, xmax//8).  `limit`: windows whose max exceeds it are skipped (the y-vs-width quirk, :194);
+// pass slide_len for the x axis.  Entries nobody writes are -1 (stay 0 in the output).
+int espnet_ds8_lut(int slide_len, int ws, int limit, int32_t* lut, int lut_len) {
+    if (!lut || slide_len <= 0 || ws <= 0 || (ws % 8) != 0 || lut_len != (int)((double)slide_len / 8)) return ESPNET_EINVAL;
+    for (int i = 0; i < lut_len; ++i) lut[i] = -1;
+    for (int k = 0; k <= slide_len / ws; ++k) {
+        const int lo = k * ws;
+        const int hi = (k == slide_len / ws) ? slide_len : (k + 1) * ws;
+        if (hi > limit) continue;
+        const int w = hi - lo;
+        if (w <= 0) continue;
+        const int dw = (int)((double)w / 8);
+        if (dw <= 0) continue;
+        const int d0 = lo / 8, d1 = hi / 8;
+        if (d1 - d0 != dw) return ESPNET_ESHAPE;   // numpy would refuse the paste in the reference too
+        const double scale = (double)w / (double)dw;
+        for (int i = 0; i < dw; ++i) {
+            int s = (int)std::floor((double)i * scale);
+            if (s > w - 1) s = w - 1;
+            lut[d0 + i] = lo + s;
+        }
+    }
+    return ESPNET_OK;
+}
+
+int espnet_downsample_lut(const uint8_t* level0, int slide_h, int slide_w, uint8_t* ds, int ds_h, int ds_w, const int32_t* ysrc_dev,
+                          const int32_t* xsrc_dev, void* stream) {
+    if (!level0 || !ds || !ysrc_dev || !xsrc_dev || slide_h <= 0 || slide_w <= 0 || ds_h <= 0 || ds_w <= 0) return ESPNET_EINVAL;
+    if (ds_h > 65535) return ESPNET_ESHAPE;
+    int gx = (ds_w + 255) / 256;
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, ds_h);
+    downsample_lut_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(level0, slide_w, ds, ds_h, ds_w, ysrc_dev, xsrc_dev);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+int espnet_confusion_hist(const uint8_t* pred, const uint8_t* gt, size_t count, int n_classes, unsigned long long* hist_dev, void* stream) {
+    if (!pred || !gt || !hist_dev || n_classes <= 0 || n_classes > 32) return ESPNET_EINVAL;
+    if (count == 0) return ESPNET_OK;
+    size_t g = (count + 256 * 64 - 1) / (256 * 64);
+    if (g > 1184) g = 1184;
+    if (g < 1) g = 1;
+    confusion_hist_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(pred, gt, count, n_classes, hist_dev);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,812 @@
+// fp32 CUDA-core kernels of the ESPNet inference path (sm_100a).
+//
+// Layout: activations are planar fp32 [B][C][H][W] (the reference's NCHW, Model.py) so that the 32
+// lanes of a warp walk consecutive x of one channel plane: every global access is a coalesced 128 B
+// line, dilated taps are plain address shifts, and concat (Model.py:157,208,350,359,368) is a
+// channel offset into a wider buffer.  Every heavy kernel uses the same register tile: one thread
+// owns 4 pixels (4 consecutive rows at one column) x all output channels of a branch, activations
+// come from global/L1 (1 coalesced load per pixel-row), weights are warp-broadcast LDS.128 from
+// shared memory, so one (tap, input-channel) step is 4 LDG + ceil(CO/4) LDS for 4*CO FFMA.
+// These kernels carry the 1e-3 logit bar (true fp32 FMA); they are FMA-bound, not HBM-bound
+// (SURVEY.md 8(d) caveat).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace espnet {
+
+constexpr int kRows = 4;  // pixels (rows) per thread in the register tile
+
+__device__ __forceinline__ float bn_prelu(float v, float s, float t, float a) {
+    v = fmaf(v, s, t);
+    return v >= 0.f ? v : a * v;
+}
+
+// acc[r][j] += a[r] * w[j], j < CO; w is a 16 B aligned shared-memory row of round_up(CO,4) floats,
+// identical for all lanes (broadcast).
+template <int CO>
+__device__ __forceinline__ void fma_tile(float (&acc)[kRows][CO], const float (&a)[kRows], const float* __restrict__ w) {
+#pragma unroll
+    for (int j4 = 0; j4 < CO / 4; ++j4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + 4 * j4);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            acc[r][4 * j4 + 0] = fmaf(a[r], wv.x, acc[r][4 * j4 + 0]);
+            acc[r][4 * j4 + 1] = fmaf(a[r], wv.y, acc[r][4 * j4 + 1]);
+            acc[r][4 * j4 + 2] = fmaf(a[r], wv.z, acc[r][4 * j4 + 2]);
+            acc[r][4 * j4 + 3] = fmaf(a[r], wv.w, acc[r][4 * j4 + 3]);
+        }
+    }
+#pragma unroll
+    for (int j = (CO / 4) * 4; j < CO; ++j) {
+        const float wv = w[j];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r][j] = fmaf(a[r], wv, acc[r][j]);
+    }
+}
+
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+
+__device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict__ src, int n) {
+    // n is a multiple of 4 and both pointers are 16 B aligned (the packer guarantees it)
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// S1 stem: P0 normalise (VisualizeResults_iou.py:107-119) + level1 CBR 3x3 s2 (Model.py:253) +
+// sample1 avg-pool (Model.py:254) + cat + b1 BR (Model.py:257,350)  ->  output0_cat [B,19,H/2,W/2]
+// plus the raw pooled image inp1 [B,3,H/2,W/2] (sample2's second pool reads it).
+// ------------------------------------------------------------------------------------------------
+struct StemParams {
+    const void* x;
+    int in_fmt, B, H, W;
+    float mean[3], stdv[3];
+    const int32_t* origins;
+    int slide_h, slide_w;
+    const float* w1;                    // [27][16]: (ci*9 + ky*3 + kx) x co
+    const float *l1_s, *l1_t, *l1_a;    // level1 BN scale/shift, PReLU slope (16)
+    const float *b1_s, *b1_t, *b1_a;    // b1 (19)
+    float* out0cat;
+    float* inp1raw;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
+    __shared__ __align__(16) float sw[27 * 16];
+    __shared__ float sp[3 * 16 + 3 * 19];
+    for (int i = threadIdx.x; i < 27 * 16; i += 256) sw[i] = p.w1[i];
+    for (int i = threadIdx.x; i < 16; i += 256) { sp[i] = p.l1_s[i]; sp[16 + i] = p.l1_t[i]; sp[32 + i] = p.l1_a[i]; }
+    for (int i = threadIdx.x; i < 19; i += 256) { sp[48 + i] = p.b1_s[i]; sp[67 + i] = p.b1_t[i]; sp[86 + i] = p.b1_a[i]; }
+    __syncthreads();
+    const int H2 = p.H >> 1, W2 = p.W >> 1;
+    const int x2 = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y2 = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x2 >= W2 || y2 >= H2) return;
+
+    long long ox = 0, oy = 0;
+    if (FMT == 2) { ox = p.origins[2 * b]; oy = p.origins[2 * b + 1]; }
+    float v[3][9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int yy = 2 * y2 - 1 + ky, xx = 2 * x2 - 1 + kx;
+            const bool in = (yy >= 0) && (yy < p.H) && (xx >= 0) && (xx < p.W);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float val = 0.f;   // conv / pool zero padding of the NORMALISED tensor (Model.py:20,230)
+                if (in) {
+                    if (FMT == 0) {
+                        val = __ldg(reinterpret_cast<const float*>(p.x) + ((size_t)(b * 3 + c) * p.H + yy) * p.W + xx);
+                    } else {
+                        unsigned int u = 0;   // outside the slide openslide pads with 0
+                        if (FMT == 1) {
+                            u = __ldg(reinterpret_cast<const unsigned char*>(p.x) + ((size_t)((size_t)b * p.H + yy) * p.W + xx) * 3 + c);
+                        } else {
+                            const long long sx = ox + xx, sy = oy + yy;
+                            if (sx >= 0 && sy >= 0 && sx < p.slide_w && sy < p.slide_h)
+                                u = __ldg(reinterpret_cast<const unsigned char*>(p.x) + ((size_t)sy * p.slide_w + sx) * 3 + c);
+                        }
+                        // three separate fp32 roundings, exactly as numpy does them
+                        val = __fdiv_rn(__fdiv_rn(__fsub_rn((float)u, p.mean[c]), p.stdv[c]), 255.f);
+                    }
+                }
+                v[c][ky * 3 + kx] = val;
+            }
+        }
+    }
+    const size_t plane = (size_t)H2 * W2;
+    const size_t pix = (size_t)y2 * W2 + x2;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float a = v[c][t];
+            const float4* w4 = reinterpret_cast<const float4*>(sw + (c * 9 + t) * 16);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 w = w4[j4];
+                acc[4 * j4 + 0] = fmaf(a, w.x, acc[4 * j4 + 0]);
+                acc[4 * j4 + 1] = fmaf(a, w.y, acc[4 * j4 + 1]);
+                acc[4 * j4 + 2] = fmaf(a, w.z, acc[4 * j4 + 2]);
+                acc[4 * j4 + 3] = fmaf(a, w.w, acc[4 * j4 + 3]);
+            }
+        }
+    float* o = p.out0cat + (size_t)b * 19 * plane + pix;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float y = bn_prelu(acc[j], sp[j], sp[16 + j], sp[32 + j]);       // level1.bn + level1.act
+        y = bn_prelu(y, sp[48 + j], sp[67 + j], sp[86 + j]);              // b1 on channels 0..15
+        o[(size_t)j * plane] = y;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) s += v[c][t];
+        s = s / 9.f;                                                      // count_include_pad: always / 9
+        p.inp1raw[(size_t)(b * 3 + c) * plane + pix] = s;
+        o[(size_t)(16 + c) * plane] = bn_prelu(s, sp[48 + 16 + c], sp[67 + 16 + c], sp[86 + 16 + c]);
+    }
+}
+
+// sample2's second AvgPool2d(3,2,1) (Model.py:255,348) fused with b2's BR on cat channels 128..130.
+__global__ void __launch_bounds__(256) pool_b2_kernel(const float* __restrict__ inp1raw, int B, int H2, int W2,
+                                                      const float* __restrict__ s, const float* __restrict__ t,
+                                                      const float* __restrict__ a, float* __restrict__ out1cat, int C1, int ch_off) {
+    const int H4 = H2 >> 1, W4 = W2 >> 1;
+    const size_t n = (size_t)B * 3 * H4 * W4;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int x = (int)(i % W4);
+        const int y = (int)((i / W4) % H4);
+        const int c = (int)((i / ((size_t)W4 * H4)) % 3);
+        const int b = (int)(i / ((size_t)W4 * H4 * 3));
+        const float* src = inp1raw + (size_t)(b * 3 + c) * H2 * W2;
+        float sum = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yy = 2 * y - 1 + ky, xx = 2 * x - 1 + kx;
+                if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) sum += __ldg(src + (size_t)yy * W2 + xx);
+            }
+        sum = sum / 9.f;
+        const int ch = ch_off + c;
+        out1cat[((size_t)b * C1 + ch) * H4 * W4 + (size_t)y * W4 + x] = bn_prelu(sum, s[ch], t[ch], a[ch]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Work decomposition shared by the reduce / branch kernels: item = (crop, 4-row strip, 32-column
+// chunk); item i goes to CTA i % gridDim.x and, inside it, to warp (i / gridDim.x) % warps, so that
+// every SM receives the same number of items (+-1) whatever the batch.
+// ------------------------------------------------------------------------------------------------
+struct TileIter {
+    int tiles_x, tiles_y, total;
+    __device__ TileIter(int B, int H, int W) {
+        tiles_x = (W + 31) >> 5;
+        tiles_y = (H + kRows - 1) / kRows;
+        total = B * tiles_x * tiles_y;
+    }
+    __device__ void decode(int item, int& b, int& y0, int& x) const {
+        const int tx = item % tiles_x;
+        const int ty = (item / tiles_x) % tiles_y;
+        b = item / (tiles_x * tiles_y);
+        y0 = ty * kRows;
+        x = tx * 32 + (threadIdx.x & 31);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// ESP reduce: 1x1 conv CIN -> CO (Model.py:178,192), o1 planar [B,CO,H,W].
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int CO>
+__global__ void __launch_bounds__(256) reduce1x1_kernel(const float* __restrict__ in, const float* __restrict__ w /*[CIN][pad4(CO)]*/,
+                                                        float* __restrict__ o1, int B, int HW) {
+    constexpr int CP = pad4(CO);
+    extern __shared__ __align__(16) float smem[];
+    copy_to_smem(smem, w, CIN * CP);
+    __syncthreads();
+    const int chunks = (HW + 127) / 128;           // a warp item = 128 consecutive pixels (4 per lane)
+    const int total = B * chunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int k = warp;; k += nwarp) {
+        const int item = k * gridDim.x + blockIdx.x;
+        if (item >= total) break;
+        const int b = item / chunks;
+        const int p0 = (item % chunks) * 128 + lane;
+        bool ok[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) ok[r] = (p0 + 32 * r) < HW;
+        float acc[kRows][CO];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+#pragma unroll
+            for (int j = 0; j < CO; ++j) acc[r][j] = 0.f;
+        const float* src = in + (size_t)b * CIN * HW + p0;
+#pragma unroll 4
+        for (int ci = 0; ci < CIN; ++ci) {
+            float a[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * HW + 32 * r) : 0.f;
+            fma_tile<CO>(acc, a, smem + ci * CP);
+        }
+        float* dst = o1 + (size_t)b * CO * HW + p0;
+#pragma unroll
+        for (int j = 0; j < CO; ++j)
+#pragma unroll
+            for (int r = 0; r < kRows; ++r)
+                if (ok[r]) dst[(size_t)j * HW + 32 * r] = acc[r][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DownSamplerB reduce: 3x3 stride-2 pad-1 conv CIN -> CO (Model.py:135,145), in [B,CIN,Hi,Wi]
+// -> o1 [B,CO,Hi/2,Wi/2].  Weights [tap][CIN][pad4(CO)] resident in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int CO>
+__global__ void __launch_bounds__(384, 1) reduce3x3s2_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                             float* __restrict__ o1, int B, int Hi, int Wi) {
+    constexpr int CP = pad4(CO);
+    extern __shared__ __align__(16) float smem[];
+    copy_to_smem(smem, w, 9 * CIN * CP);
+    __syncthreads();
+    const int Ho = Hi >> 1, Wo = Wi >> 1;
+    const size_t iplane = (size_t)Hi * Wi, oplane = (size_t)Ho * Wo;
+    const TileIter it(B, Ho, Wo);
+    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int k = warp;; k += nwarp) {
+        const int item = k * gridDim.x + blockIdx.x;
+        if (item >= it.total) break;
+        int b, y0, x;
+        it.decode(item, b, y0, x);
+        float acc[kRows][CO];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+#pragma unroll
+            for (int j = 0; j < CO; ++j) acc[r][j] = 0.f;
+        const float* src = in + (size_t)b * CIN * iplane;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            const int xi = 2 * x - 1 + kx;
+            const bool xok = (x < Wo) && (xi >= 0) && (xi < Wi);
+            int off[kRows];
+            bool ok[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const int yi = 2 * (y0 + r) - 1 + ky;
+                ok[r] = xok && (y0 + r < Ho) && (yi >= 0) && (yi < Hi);
+                off[r] = ok[r] ? yi * Wi + xi : 0;
+            }
+            const float* wt = smem + tap * CIN * CP;
+#pragma unroll 4
+            for (int ci = 0; ci < CIN; ++ci) {
+                float a[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * iplane + off[r]) : 0.f;
+                fma_tile<CO>(acc, a, wt + ci * CP);
+            }
+        }
+        if (x < Wo) {
+            float* dst = o1 + (size_t)b * CO * oplane + (size_t)y0 * Wo + x;
+#pragma unroll
+            for (int j = 0; j < CO; ++j)
+#pragma unroll
+                for (int r = 0; r < kRows; ++r)
+                    if (y0 + r < Ho) dst[(size_t)j * oplane + (size_t)r * Wo] = acc[r][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The ESP "split-transform-merge" stage shared by DownSamplerB (Model.py:146-159) and
+// DilatedParllelResidualBlockB (Model.py:194-213): five dilated 3x3 branches on o1 (d=1,2,4,8,16),
+// hierarchical-feature-fusion adds, concat (channel offsets), optional residual add BEFORE BN,
+// folded BN + PReLU, and (tight fusion) an optional second BN + PReLU that writes the result
+// straight into the following concat buffer (b2 / b3 of Model.py:263,269).
+// The HFF running sum add_k = add_{k-1} + d_{2^k} is the accumulator itself: the chain branches
+// keep accumulating into the same registers and each partial sum is emitted as one concat slice.
+// ------------------------------------------------------------------------------------------------
+struct BranchParams {
+    const float* o1;        // [B,N,H,W]
+    const float* w_d1;      // [9][N][pad4(CO1)]
+    const float* w_chain;   // [4][9][N][pad4(CO)]   (d2,d4,d8,d16)
+    const float* res;       // [B,C,H,W] residual input or nullptr
+    const float *s, *t, *a; // own BN scale/shift + PReLU slope (C)
+    float* out;             // [B,C,H,W] or nullptr
+    const float *s2, *t2, *a2;  // second BR, indexed by the cat channel
+    float* out2;            // [B,C2,H,W] or nullptr
+    int C2, c2_off;
+    int B, H, W;
+};
+
+template <int N, int CO1, int CO>
+__global__ void __launch_bounds__(384, 1) esp_branch_kernel(const BranchParams p) {
+    constexpr int C = CO1 + 4 * CO;
+    constexpr int CP1 = pad4(CO1), CP = pad4(CO);
+    constexpr int W1 = 9 * N * CP1, WC = 4 * 9 * N * CP;
+    extern __shared__ __align__(16) float smem[];
+    float* sw1 = smem;
+    float* swc = smem + W1;
+    float* sep = swc + WC;   // 6*C epilogue params
+    copy_to_smem(sw1, p.w_d1, W1);
+    copy_to_smem(swc, p.w_chain, WC);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        sep[i] = p.s[i]; sep[C + i] = p.t[i]; sep[2 * C + i] = p.a[i];
+        if (p.out2) {
+            sep[3 * C + i] = p.s2[p.c2_off + i]; sep[4 * C + i] = p.t2[p.c2_off + i]; sep[5 * C + i] = p.a2[p.c2_off + i];
+        }
+    }
+    __syncthreads();
+    const int H = p.H, W = p.W;
+    const size_t plane = (size_t)H * W;
+    const TileIter it(p.B, H, W);
+    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+
+    for (int k = warp;; k += nwarp) {
+        const int item = k * gridDim.x + blockIdx.x;
+        if (item >= it.total) break;
+        int b, y0, x;
+        it.decode(item, b, y0, x);
+        const float* src = p.o1 + (size_t)b * N * plane;
+        const size_t pix0 = (size_t)y0 * W + x;
+
+        // ---- branch d1: CO1 outputs ---------------------------------------------------------------
+        {
+            float acc[kRows][CO1];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r)
+#pragma unroll
+                for (int j = 0; j < CO1; ++j) acc[r][j] = 0.f;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap - 3 * ky;
+                const int xi = x + (kx - 1);
+                const bool xok = (x < W) && (xi >= 0) && (xi < W);
+                int off[kRows];
+                bool ok[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) {
+                    const int yi = y0 + r + (ky - 1);
+                    ok[r] = xok && (yi >= 0) && (yi < H);
+                    off[r] = ok[r] ? yi * W + xi : 0;
+                }
+                const float* wt = sw1 + tap * N * CP1;
+#pragma unroll 4
+                for (int ci = 0; ci < N; ++ci) {
+                    float a[kRows];
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * plane + off[r]) : 0.f;
+                    fma_tile<CO1>(acc, a, wt + ci * CP1);
+                }
+            }
+            if (x < W) {
+#pragma unroll
+                for (int j = 0; j < CO1; ++j)
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        if (y0 + r >= H) continue;
+                        const size_t o = ((size_t)b * C + j) * plane + pix0 + (size_t)r * W;
+                        float v = acc[r][j];
+                        if (p.res) v += __ldg(p.res + o);
+                        v = bn_prelu(v, sep[j], sep[C + j], sep[2 * C + j]);
+                        if (p.out) p.out[o] = v;
+                        if (p.out2)
+                            p.out2[((size_t)b * p.C2 + p.c2_off + j) * plane + pix0 + (size_t)r * W] =
+                                bn_prelu(v, sep[3 * C + j], sep[4 * C + j], sep[5 * C + j]);
+                    }
+            }
+        }
+        // ---- chain d2 -> d4 -> d8 -> d16 with the HFF sum living in the accumulator -----------------
+        {
+            float acc[kRows][CO];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r)
+#pragma unroll
+                for (int j = 0; j < CO; ++j) acc[r][j] = 0.f;
+#pragma unroll 1
+            for (int br = 0; br < 4; ++br) {
+                const int d = 2 << br;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+                    const int xi = x + (kx - 1) * d;
+                    const bool xok = (x < W) && (xi >= 0) && (xi < W);
+                    int off[kRows];
+                    bool ok[kRows];
+                    bool any = false;
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        const int yi = y0 + r + (ky - 1) * d;
+                        ok[r] = xok && (yi >= 0) && (yi < H);
+                        off[r] = ok[r] ? yi * W + xi : 0;
+                        any |= ok[r];
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;   // whole warp's tap lies in the zero padding
+                    const float* wt = swc + (br * 9 + tap) * N * CP;
+#pragma unroll 4
+                    for (int ci = 0; ci < N; ++ci) {
+                        float a[kRows];
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * plane + off[r]) : 0.f;
+                        fma_tile<CO>(acc, a, wt + ci * CP);
+                    }
+                }
+                if (x < W) {
+                    const int ch0 = CO1 + br * CO;
+#pragma unroll
+                    for (int j = 0; j < CO; ++j)
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) {
+                            if (y0 + r >= H) continue;
+                            const int ch = ch0 + j;
+                            const size_t o = ((size_t)b * C + ch) * plane + pix0 + (size_t)r * W;
+                            float v = acc[r][j];
+                            if (p.res) v += __ldg(p.res + o);
+                            v = bn_prelu(v, sep[ch], sep[C + ch], sep[2 * C + ch]);
+                            if (p.out) p.out[o] = v;
+                            if (p.out2)
+                                p.out2[((size_t)b * p.C2 + p.c2_off + ch) * plane + pix0 + (size_t)r * W] =
+                                    bn_prelu(v, sep[3 * C + ch], sep[4 * C + ch], sep[5 * C + ch]);
+                        }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder / head kernels.  NC = classes.
+// ------------------------------------------------------------------------------------------------
+// S7: b3 output -> encoder.classifier 1x1 (Model.py:271,302); FULL net additionally applies `br`
+// (BN, no activation, Model.py:331) and up_l3 ConvTranspose2d k2 s2 (Model.py:334,370):
+// out[o][2y+a][2x+b] = sum_c v[c] * Wt[c][o][a][b].
+template <int NC>
+struct Head3Params {
+    const float* in;     // out2cat [B,256,H8,W8]
+    const float* w;      // [256][NC]
+    const float *bn_s, *bn_t;   // br (NC)
+    const float* wt;     // up_l3 [NC][NC][2][2]
+    float* enc_out;      // [B,NC,H8,W8] or nullptr
+    float* up_out;       // [B,NC,2*H8,2*W8] or nullptr
+    int B, H8, W8;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256) head3_kernel(const Head3Params<NC> p) {
+    __shared__ float sw[256 * NC];
+    __shared__ float swt[NC * NC * 4];
+    __shared__ float sbn[2 * NC];
+    for (int i = threadIdx.x; i < 256 * NC; i += 256) sw[i] = p.w[i];
+    if (p.up_out) {
+        for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
+        for (int i = threadIdx.x; i < NC; i += 256) { sbn[i] = p.bn_s[i]; sbn[NC + i] = p.bn_t[i]; }
+    }
+    __syncthreads();
+    const size_t plane = (size_t)p.H8 * p.W8;
+    const size_t n = (size_t)p.B * plane;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int b = (int)(i / plane);
+        const size_t pix = i % plane;
+        const float* src = p.in + (size_t)b * 256 * plane + pix;
+        float acc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+#pragma unroll 8
+        for (int ci = 0; ci < 256; ++ci) {
+            const float a = __ldg(src + (size_t)ci * plane);
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[j] = fmaf(a, sw[ci * NC + j], acc[j]);
+        }
+        if (p.enc_out) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) p.enc_out[((size_t)b * NC + j) * plane + pix] = acc[j];
+        }
+        if (p.up_out) {
+            const int y = (int)(pix / p.W8), x = (int)(pix % p.W8);
+            const int W4 = 2 * p.W8;
+            const size_t plane4 = 4 * plane;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[j] = fmaf(acc[j], sbn[j], sbn[NC + j]);
+#pragma unroll
+            for (int o = 0; o < NC; ++o) {
+                float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const float* wq = swt + (c * NC + o) * 4;
+                    r00 = fmaf(acc[c], wq[0], r00); r01 = fmaf(acc[c], wq[1], r01);
+                    r10 = fmaf(acc[c], wq[2], r10); r11 = fmaf(acc[c], wq[3], r11);
+                }
+                float* d = p.up_out + ((size_t)b * NC + o) * plane4 + (size_t)(2 * y) * W4 + 2 * x;
+                *reinterpret_cast<float2*>(d) = make_float2(r00, r01);
+                *reinterpret_cast<float2*>(d + W4) = make_float2(r10, r11);
+            }
+        }
+    }
+}
+
+// S8 + first half of S9: level3_C 1x1 131->NC on output1_cat (Model.py:330,372), cat with up_l3's
+// output (Model.py:373) and combine_l2_l3[0] BR(2NC) -> t [B,2NC,H4,W4].
+template <int NC>
+struct DecAParams {
+    const float* out1cat;   // [B,131,H4,W4]
+    const float* up3;       // [B,NC,H4,W4]
+    const float* w;         // [131][NC]
+    const float *s, *t, *a; // BR over 2NC
+    float* tout;            // [B,2NC,H4,W4]
+    int B, H4, W4;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256) dec_a_kernel(const DecAParams<NC> p) {
+    __shared__ float sw[131 * NC];
+    __shared__ float sb[6 * NC];
+    for (int i = threadIdx.x; i < 131 * NC; i += 256) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < 2 * NC; i += 256) { sb[i] = p.s[i]; sb[2 * NC + i] = p.t[i]; sb[4 * NC + i] = p.a[i]; }
+    __syncthreads();
+    const size_t plane = (size_t)p.H4 * p.W4;
+    const size_t n = (size_t)p.B * plane;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int b = (int)(i / plane);
+        const size_t pix = i % plane;
+        const float* src = p.out1cat + (size_t)b * 131 * plane + pix;
+        float acc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+#pragma unroll 8
+        for (int ci = 0; ci < 131; ++ci) {
+            const float a = __ldg(src + (size_t)ci * plane);
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[j] = fmaf(a, sw[ci * NC + j], acc[j]);
+        }
+        float* d = p.tout + (size_t)b * 2 * NC * plane + pix;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) d[(size_t)j * plane] = bn_prelu(acc[j], sb[j], sb[2 * NC + j], sb[4 * NC + j]);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const float v = __ldg(p.up3 + ((size_t)b * NC + j) * plane + pix);
+            d[(size_t)(NC + j) * plane] = bn_prelu(v, sb[NC + j], sb[3 * NC + j], sb[5 * NC + j]);
+        }
+    }
+}
+
+// Second half of S9: combine_l2_l3[1] CBR 3x3 2NC->NC (Model.py:335) + up_l2 = ConvT k2 s2 + BR(NC)
+// (Model.py:337) -> comb [B,NC,H2,W2].
+template <int NC>
+struct DecBParams {
+    const float* tin;       // [B,2NC,H4,W4]
+    const float* w;         // [2NC][9][NC]
+    const float *s, *t, *a; // CBR BN + PReLU (NC)
+    const float* wt;        // up_l2.0 [NC][NC][2][2]
+    const float *s2, *t2, *a2;  // up_l2.1 BR (NC)
+    float* comb;            // [B,NC,H2,W2]
+    int B, H4, W4;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256) dec_b_kernel(const DecBParams<NC> p) {
+    __shared__ float sw[2 * NC * 9 * NC];
+    __shared__ float swt[NC * NC * 4];
+    __shared__ float sb[6 * NC];
+    for (int i = threadIdx.x; i < 2 * NC * 9 * NC; i += 256) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
+    for (int i = threadIdx.x; i < NC; i += 256) {
+        sb[i] = p.s[i]; sb[NC + i] = p.t[i]; sb[2 * NC + i] = p.a[i];
+        sb[3 * NC + i] = p.s2[i]; sb[4 * NC + i] = p.t2[i]; sb[5 * NC + i] = p.a2[i];
+    }
+    __syncthreads();
+    const int H4 = p.H4, W4 = p.W4;
+    const size_t plane = (size_t)H4 * W4;
+    const size_t n = (size_t)p.B * plane;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int b = (int)(i / plane);
+        const int pix = (int)(i % plane);
+        const int y = pix / W4, x = pix % W4;
+        const float* src = p.tin + (size_t)b * 2 * NC * plane;
+        float acc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            if (yy < 0 || yy >= H4 || xx < 0 || xx >= W4) continue;
+            const size_t o = (size_t)yy * W4 + xx;
+#pragma unroll 2
+            for (int ci = 0; ci < 2 * NC; ++ci) {
+                const float a = __ldg(src + (size_t)ci * plane + o);
+                const float* wr = sw + (ci * 9 + tap) * NC;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[j] = bn_prelu(acc[j], sb[j], sb[NC + j], sb[2 * NC + j]);
+        const int W2 = 2 * W4;
+        const size_t plane2 = 4 * plane;
+#pragma unroll
+        for (int o = 0; o < NC; ++o) {
+            float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float* wq = swt + (c * NC + o) * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) r[q] = fmaf(acc[c], wq[q], r[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[q] = bn_prelu(r[q], sb[3 * NC + o], sb[4 * NC + o], sb[5 * NC + o]);
+            float* d = p.comb + ((size_t)b * NC + o) * plane2 + (size_t)(2 * y) * W2 + 2 * x;
+            *reinterpret_cast<float2*>(d) = make_float2(r[0], r[1]);
+            *reinterpret_cast<float2*>(d + W2) = make_float2(r[2], r[3]);
+        }
+    }
+}
+
+// S10: `conv` CBR 3x3 (NC+19)->NC on cat[comb, output0_cat] (Model.py:332,375) + classifier
+// ConvT k2 s2 (Model.py:339,377) -> logits [B,NC,H,W]; fused epilogues: arg-max mask
+// (VisualizeResults_iou.py:128, ties -> lowest index) and softmax accumulation (ensemble extension).
+template <int NC>
+struct DecCParams {
+    const float* comb;      // [B,NC,H2,W2]
+    const float* out0cat;   // [B,19,H2,W2]
+    const float* w;         // [(NC+19)][9][NC]
+    const float *s, *t, *a; // conv BN + PReLU
+    const float* wt;        // classifier [NC][NC][2][2]
+    float* logits;          // [B,NC,H,W] or nullptr
+    unsigned char* mask;    // [B,H,W] or nullptr
+    float* prob_acc;        // [B,NC,H,W] or nullptr
+    int prob_init, mask_from_prob;
+    int B, H2, W2;
+};
+
+template <int NC>
+__device__ __forceinline__ int argmax_first(const float (&v)[NC]) {
+    int best = 0;
+    float bv = v[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j)
+        if (v[j] > bv) { bv = v[j]; best = j; }
+    return best;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) dec_c_kernel(const DecCParams<NC> p) {
+    constexpr int CI = NC + 19;
+    __shared__ float sw[CI * 9 * NC];
+    __shared__ float swt[NC * NC * 4];
+    __shared__ float sb[3 * NC];
+    for (int i = threadIdx.x; i < CI * 9 * NC; i += 256) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
+    for (int i = threadIdx.x; i < NC; i += 256) { sb[i] = p.s[i]; sb[NC + i] = p.t[i]; sb[2 * NC + i] = p.a[i]; }
+    __syncthreads();
+    const int H2 = p.H2, W2 = p.W2;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x >= W2 || y >= H2) return;
+    const size_t plane = (size_t)H2 * W2;
+    float acc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy >= H2 || xx < 0 || xx >= W2) continue;
+        const size_t o = (size_t)yy * W2 + xx;
+        const float* s0 = p.comb + (size_t)b * NC * plane + o;
+#pragma unroll
+        for (int ci = 0; ci < NC; ++ci) {
+            const float a = __ldg(s0 + (size_t)ci * plane);
+            const float* wr = sw + (ci * 9 + tap) * NC;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+        }
+        const float* s1 = p.out0cat + (size_t)b * 19 * plane + o;
+#pragma unroll
+        for (int ci = 0; ci < 19; ++ci) {
+            const float a = __ldg(s1 + (size_t)ci * plane);
+            const float* wr = sw + ((NC + ci) * 9 + tap) * NC;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = bn_prelu(acc[j], sb[j], sb[NC + j], sb[2 * NC + j]);
+    const int W = 2 * W2;
+    const size_t fplane = 4 * plane;
+    float lg[4][NC];   // the 2x2 output pixels x classes
+#pragma unroll
+    for (int o = 0; o < NC; ++o) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) lg[q][o] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float* wq = swt + (c * NC + o) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) lg[q][o] = fmaf(acc[c], wq[q], lg[q][o]);
+        }
+    }
+    const size_t base = (size_t)(2 * y) * W + 2 * x;
+    if (p.logits) {
+#pragma unroll
+        for (int o = 0; o < NC; ++o) {
+            float* d = p.logits + ((size_t)b * NC + o) * fplane + base;
+            *reinterpret_cast<float2*>(d) = make_float2(lg[0][o], lg[1][o]);
+            *reinterpret_cast<float2*>(d + W) = make_float2(lg[2][o], lg[3][o]);
+        }
+    }
+    int am[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) am[q] = argmax_first<NC>(lg[q]);
+    if (p.prob_acc) {
+        float pr[4][NC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float m = lg[q][0];
+#pragma unroll
+            for (int o = 1; o < NC; ++o) m = fmaxf(m, lg[q][o]);
+            float sum = 0.f;
+#pragma unroll
+            for (int o = 0; o < NC; ++o) { pr[q][o] = expf(lg[q][o] - m); sum += pr[q][o]; }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int o = 0; o < NC; ++o) pr[q][o] *= inv;
+        }
+#pragma unroll
+        for (int o = 0; o < NC; ++o) {
+            float* d = p.prob_acc + ((size_t)b * NC + o) * fplane + base;
+            float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+            if (!p.prob_init) { t0 = *reinterpret_cast<float2*>(d); t1 = *reinterpret_cast<float2*>(d + W); }
+            pr[0][o] += t0.x; pr[1][o] += t0.y; pr[2][o] += t1.x; pr[3][o] += t1.y;
+            *reinterpret_cast<float2*>(d) = make_float2(pr[0][o], pr[1][o]);
+            *reinterpret_cast<float2*>(d + W) = make_float2(pr[2][o], pr[3][o]);
+        }
+        if (p.mask_from_prob) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) am[q] = argmax_first<NC>(pr[q]);
+        }
+    }
+    if (p.mask) {
+        unsigned char* d = p.mask + (size_t)b * fplane + base;
+        *reinterpret_cast<uchar2*>(d) = make_uchar2((unsigned char)am[0], (unsigned char)am[1]);
+        *reinterpret_cast<uchar2*>(d + W) = make_uchar2((unsigned char)am[2], (unsigned char)am[3]);
+    }
+}
+
+// ESPNet-C tail: nn.Upsample(scale_factor=8, mode='bilinear', align_corners=False)
+// (VisualizeResults_iou.py:258-261,125-126) + arg-max (:128) of encoder logits [B,NC,H8,W8].
+template <int NC>
+__global__ void __launch_bounds__(256) upsample8_argmax_kernel(const float* __restrict__ enc, int B, int H8, int W8,
+                                                               unsigned char* __restrict__ mask, float* __restrict__ up_logits) {
+    const int H = 8 * H8, W = 8 * W8;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    // area_pixel_compute_source_index(scale=1/8, align_corners=False): src = (dst+0.5)/8-0.5, clamped at 0
+    float sy = 0.125f * ((float)y + 0.5f) - 0.5f; sy = sy < 0.f ? 0.f : sy;
+    float sx = 0.125f * ((float)x + 0.5f) - 0.5f; sx = sx < 0.f ? 0.f : sx;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H8 - 1 ? 1 : 0), x1 = x0 + (x0 < W8 - 1 ? 1 : 0);
+    const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+    const size_t plane = (size_t)H8 * W8;
+    float v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const float* s = enc + ((size_t)b * NC + c) * plane;
+        const float v00 = __ldg(s + (size_t)y0 * W8 + x0), v01 = __ldg(s + (size_t)y0 * W8 + x1);
+        const float v10 = __ldg(s + (size_t)y1 * W8 + x0), v11 = __ldg(s + (size_t)y1 * W8 + x1);
+        v[c] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+        if (up_logits) up_logits[((size_t)b * NC + c) * H * W + (size_t)y * W + x] = v[c];
+    }
+    if (mask) mask[(size_t)b * H * W + (size_t)y * W + x] = (unsigned char)argmax_first<NC>(v);
+}
+
+}  // namespace espnet

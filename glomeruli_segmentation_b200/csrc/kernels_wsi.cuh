@@ -1,0 +1,123 @@
+// Integer / byte kernels either side of the forward: tile -> slide stitching (T3), /8 nearest
+// down-sample (T4) and the confusion-matrix histogram (IOUEval.py).  All index arithmetic that
+// involves Python float semantics (T1 strides, cv2 nearest scale) is done on the host in double and
+// handed to these kernels as integers / LUTs, so results are bit-exact by construction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace espnet {
+
+// T3, scatter form, arbitrary boxes (eval_wsi_segmentation.py:259-316): one CTA column per box, one
+// thread per aligned 32-bit word of the slide row segment the box covers; the four class bytes are
+// max-merged with __vmaxu4 under an atomicCAS loop (max is commutative / idempotent, so the result
+// does not depend on the order boxes land in).
+__global__ void __launch_bounds__(256) stitch_boxes_kernel(unsigned char* __restrict__ slide, int SH, int SW, int y_limit,
+                                                           const int32_t* __restrict__ boxes, const long long* __restrict__ offs,
+                                                           const unsigned char* __restrict__ masks, int n_boxes) {
+    const int bi = blockIdx.x;
+    if (bi >= n_boxes) return;
+    const int x0 = boxes[4 * bi], y0 = boxes[4 * bi + 1], x1 = boxes[4 * bi + 2], y1 = boxes[4 * bi + 3];
+    const int bw = x1 - x0;
+    const int cx0 = max(x0, 0), cx1 = min(x1, SW);
+    const int cy0 = max(y0, 0), cy1 = min(min(y1, SH), y_limit);
+    if (cx1 <= cx0 || cy1 <= cy0) return;
+    const unsigned char* m = masks + offs[bi];
+    unsigned int* words = reinterpret_cast<unsigned int*>(slide);
+    for (int y = cy0 + blockIdx.y; y < cy1; y += gridDim.y) {
+        const size_t row = (size_t)y * SW;
+        const size_t f0 = row + cx0, f1 = row + cx1;          // flat byte range [f0,f1)
+        const size_t w0 = f0 >> 2, w1 = (f1 - 1) >> 2;
+        const unsigned char* mrow = m + (size_t)(y - y0) * bw;        // mrow[x - x0] for slide column x
+        for (size_t w = w0 + threadIdx.x; w <= w1; w += 256) {
+            unsigned int cand = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const size_t f = 4 * w + k;
+                if (f >= f0 && f < f1) cand |= (unsigned int)mrow[(int)(f - row) - x0] << (8 * k);
+            }
+            if (cand == 0) continue;
+            unsigned int old = words[w];
+            while (true) {
+                const unsigned int nv = __vmaxu4(old, cand);
+                if (nv == old) break;
+                const unsigned int prev = atomicCAS(words + w, old, nv);
+                if (prev == old) break;
+                old = prev;
+            }
+        }
+    }
+}
+
+// T3, gather form for the regular T1 grid (detect_glomus_test.py:268-271): tile k = j*n_x + i sits at
+// (i*stride_x, j*stride_y); each thread owns one slide pixel and takes the max over the (at most
+// ceil(win/stride)^2) tiles that cover it.  Only tile rows [row0,row0+rows) are resident (multi-GPU
+// band sharding); pixels no resident tile covers are left untouched.
+__global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restrict__ slide, int SH, int SW, int y_limit,
+                                                          const unsigned char* __restrict__ tiles, int n_x, int n_y,
+                                                          int win_x, int win_y, int sx, int sy, int row0, int rows) {
+    const int ylo = row0 * sy;
+    const int yhi = min(min((row0 + rows - 1) * sy + win_y, SH), y_limit);
+    const int y = ylo + blockIdx.y;
+    if (y >= yhi) return;
+    const int j_hi = min(min(y / sy, n_y - 1), row0 + rows - 1);
+    int j_lo = (y - win_y + sy) / sy;                 // ceil((y - win_y + 1) / sy) for y-win_y+1 > 0
+    if (y - win_y + 1 <= 0) j_lo = 0;
+    j_lo = max(j_lo, row0);
+    const size_t tile_sz = (size_t)win_x * win_y;
+    for (int x = blockIdx.x * 256 + threadIdx.x; x < SW; x += gridDim.x * 256) {
+        const int i_hi = min(x / sx, n_x - 1);
+        int i_lo = (x - win_x + sx) / sx;
+        if (x - win_x + 1 <= 0) i_lo = 0;
+        int best = -1;
+        for (int j = j_lo; j <= j_hi; ++j) {
+            const int ty = y - j * sy;
+            if (ty < 0 || ty >= win_y) continue;
+            for (int i = i_lo; i <= i_hi; ++i) {
+                const int tx = x - i * sx;
+                if (tx < 0 || tx >= win_x) continue;
+                const int v = tiles[((size_t)(j - row0) * n_x + i) * tile_sz + (size_t)ty * win_x + tx];
+                best = max(best, v);
+            }
+        }
+        if (best >= 0) {
+            unsigned char* d = slide + (size_t)y * SW + x;
+            *d = (unsigned char)max((int)*d, best);
+        }
+    }
+}
+
+// T4 (eval_wsi_segmentation.py:228,236-240): ds[y][x] = level0[ysrc[y]][xsrc[x]], 0 where a LUT entry < 0.
+__global__ void __launch_bounds__(256) downsample_lut_kernel(const unsigned char* __restrict__ level0, int SW,
+                                                             unsigned char* __restrict__ ds, int dh, int dw,
+                                                             const int32_t* __restrict__ ysrc, const int32_t* __restrict__ xsrc) {
+    const int y = blockIdx.y;
+    if (y >= dh) return;
+    const int ys = ysrc[y];
+    for (int x = blockIdx.x * 256 + threadIdx.x; x < dw; x += gridDim.x * 256) {
+        const int xs = xsrc[x];
+        ds[(size_t)y * dw + x] = (ys >= 0 && xs >= 0) ? level0[(size_t)ys * SW + xs] : (unsigned char)0;
+    }
+}
+
+// IOUEval.py:19-21 fast_hist: hist[n*gt + pred] += 1 for 0 <= gt < n  (pred >= n is a caller bug in the
+// reference -- np.bincount would grow the array and reshape would throw; here such pixels are dropped).
+__global__ void __launch_bounds__(256) confusion_hist_kernel(const unsigned char* __restrict__ pred, const unsigned char* __restrict__ gt,
+                                                             size_t count, int n, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int sh[32 * 32];
+    for (int i = threadIdx.x; i < n * n; i += 256) sh[i] = 0;
+    __syncthreads();
+    // each CTA handles a bounded slice so the 32-bit shared counters cannot overflow
+    const size_t per_cta = (count + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per_cta;
+    const size_t hi = lo + per_cta < count ? lo + per_cta : count;
+    for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+        const int g = gt[i], p = pred[i];
+        if (g < n && p < n) atomicAdd(&sh[g * n + p], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += 256)
+        if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
+
+}  // namespace espnet

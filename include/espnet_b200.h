@@ -1,0 +1,149 @@
+/*
+ * espnet_b200.h -- C ABI of libespnet_b200.so: hand-written sm_100a CUDA kernels for the ESPNet
+ * glomerular-segmentation inference hot path of jinseikenai/glomeruli_segmentation.
+ *
+ * Nothing like this ABI exists in the reference (it is 100 % Python on top of PyTorch); each entry
+ * point names the reference code it replaces (paths relative to the reference root).
+ * Plain pointers and sizes only -- no torch types.  All device pointers are raw CUDA device
+ * pointers owned by the caller; the library owns only its packed-weight buffer.  Every function
+ * returns 0 (ESPNET_OK) or a negative ESPNET_E* code; espnet_last_error() gives the message.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream); all forward / stitch calls
+ * are asynchronous on it.  There is no CPU and no cuDNN fallback anywhere behind this header.
+ */
+#ifndef ESPNET_B200_H_
+#define ESPNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ESPNET_API __attribute__((visibility("default")))
+#else
+#define ESPNET_API
+#endif
+
+#define ESPNET_OK 0
+#define ESPNET_EINVAL (-1)   /* bad argument / null pointer                        */
+#define ESPNET_ESHAPE (-2)   /* unsupported shape (H,W not multiples of 8, ...)    */
+#define ESPNET_ECUDA (-3)    /* CUDA runtime error (message has the cudaError)     */
+#define ESPNET_ESTATE (-4)   /* weights not packed / workspace too small           */
+#define ESPNET_EMISSING (-5) /* a state_dict tensor is missing or has a wrong shape */
+
+typedef struct espnet_handle espnet_t;
+
+/* One state_dict entry: name exactly as in the reference checkpoint,
+ * host pointer to contiguous fp32 data, shape.  num_batches_tracked entries may be omitted. */
+typedef struct {
+    const char* name;
+    const float* data;   /* HOST pointer, fp32, contiguous */
+    int ndim;
+    int64_t shape[4];
+} espnet_tensor_desc;
+
+/* input formats of espnet_forward */
+#define ESPNET_IN_F32_NCHW 0    /* normalised fp32 [B,3,H,W]  (what Model.py:341 receives)                    */
+#define ESPNET_IN_U8_BGR_HWC 1  /* raw u8 [B,H,W,3] BGR + mean/std: P0 fused (VisualizeResults_iou.py:107-119) */
+#define ESPNET_IN_U8_SLIDE 2    /* tiles read straight out of a resident u8 [SH,SW,3] slide at origins[B][2]   */
+
+/* compute modes */
+#define ESPNET_MODE_FP32 0      /* fp32 CUDA-core FMA everywhere: logits within 1e-3 of the reference          */
+#define ESPNET_MODE_F16TC 1     /* fp16 storage + tcgen05 (kind::f16, fp32 accumulate) ESP blocks: mask parity  */
+
+/* what the network is: full ESPNet (Model.py:306) or ESPNet-C encoder only (Model.py:242) */
+#define ESPNET_NET_FULL 0
+#define ESPNET_NET_ENCODER 1
+
+typedef struct {
+    /* ---- input ---- */
+    const void* x;        /* device pointer, format in_fmt                                                  */
+    int in_fmt;
+    int B, H, W;          /* crops, crop height/width (multiples of 8)                                      */
+    float mean[3];        /* BGR mean / std for the u8 formats (README.md:243-249)                          */
+    float std_[3];
+    const int32_t* origins; /* device [B][2] (x0,y0) for ESPNET_IN_U8_SLIDE (T1, detect_glomus_test.py:270-271) */
+    int slide_h, slide_w;   /* slide size for ESPNET_IN_U8_SLIDE; pixels outside are 0 (openslide padding)      */
+    /* ---- outputs (any may be NULL) ---- */
+    float* logits;        /* fp32 NCHW [B,classes,H,W] (FULL) or [B,classes,H/8,W/8] (ENCODER)              */
+    uint8_t* mask;        /* u8 [B,H,W] arg-max, ties -> lowest class (VisualizeResults_iou.py:128); for the
+                             ENCODER net the logits are first x8 bilinearly up-sampled (:125-126, :258-261)  */
+    float* prob_acc;      /* fp32 NCHW [B,classes,H,W]: softmax(logits) is ADDED here (ensemble extension)   */
+    int prob_init;        /* 1: overwrite prob_acc instead of adding (first fold)                            */
+    int mask_from_prob;   /* 1: mask = argmax(prob_acc after this call's add) instead of argmax(logits)      */
+    /* ---- scratch ---- */
+    void* workspace;      /* device, >= espnet_workspace_bytes(...)                                         */
+    size_t workspace_bytes;
+    void* stream;         /* cudaStream_t                                                                   */
+} espnet_forward_args;
+
+/* Replaces Model.ESPNet(classes,p,q) / Model.ESPNet_Encoder(classes,p,q) construction (Model.py:246,311). */
+ESPNET_API int espnet_create(int classes, int p, int q, int net, int device, espnet_t** out);
+ESPNET_API void espnet_destroy(espnet_t* h);
+ESPNET_API const char* espnet_last_error(const espnet_t* h); /* h may be NULL: last error of failed create */
+
+/* Replaces load_state_dict (VisualizeResults_iou.py:267,279): folds eval-mode BN (eps 1e-3) into
+ * per-channel scale/shift in fp64, re-lays conv weights for the kernels, uploads.  For the ENCODER net
+ * names carry no "encoder." prefix (Model.py:242 key set), for the FULL net they do. */
+ESPNET_API int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n);
+
+ESPNET_API int espnet_set_mode(espnet_t* h, int mode);            /* ESPNET_MODE_* ; default FP32 */
+ESPNET_API size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W);
+
+/* Replaces `img_out = model(img_variable)` (+ normalise before, arg-max after):
+ * VisualizeResults_iou.py:107-128 -> Model.py:341-378 (FULL) / :273-304 (ENCODER). */
+ESPNET_API int espnet_forward(espnet_t* h, const espnet_forward_args* a);
+
+/* Debug / parity taps: copies an internal stage of the LAST forward to `dst` (device, fp32 NCHW).
+ * stage names follow the reference module names ("b1","level2_0","level2.1","b2","level3_0",
+ * "level3.7","b3", "up_l3", "combine_l2_l3", "up_l2", "conv", ...).  *count receives elements. */
+ESPNET_API int espnet_read_stage(espnet_t* h, const char* stage, float* dst, size_t dst_elems, size_t* count, void* stream);
+
+/* Per-kernel timing for the roofline report: while on, every kernel launch of espnet_forward is bracketed
+ * by CUDA events on the launching stream.  espnet_get_profile synchronises on them and returns, per kernel
+ * name (64-byte slots in `names`), the summed device time and the launch count since profiling was switched on. */
+ESPNET_API int espnet_set_profiling(espnet_t* h, int on);
+ESPNET_API int espnet_get_profile(espnet_t* h, char* names, float* total_ms, int* launches, int max_entries, int* n_entries);
+
+/* Host-buffer convenience (the call a reference user makes per crop, batched): pageable or pinned
+ * HOST u8 BGR crops in, HOST u8 masks out; H2D, forward, D2H and the stream sync all inside. */
+ESPNET_API int espnet_segment_host(espnet_t* h, const uint8_t* crops_host, int B, int H, int W,
+                        const float mean[3], const float std_[3], uint8_t* masks_host);
+
+/* ---------------- tile -> slide stitching (eval_wsi_segmentation.py:162-316) ---------------- */
+
+/* T3 (eval_wsi_segmentation.py:259-316, annotation_handler.py:74-105): slide[y,x] = max(slide[y,x], mask_b[..])
+ * for every box b = boxes[b] = (x0,y0,x1,y1) int32 level-0 px (may overhang the slide), masks packed
+ * back to back (box b at mask_offsets[b], row pitch x1-x0).  Rows >= y_limit are left untouched
+ * (the reference's `ymax > slide_width` window skip, :194).  slide must be zero-initialised by the caller. */
+ESPNET_API int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit,
+                        const int32_t* boxes, const int64_t* mask_offsets, const uint8_t* masks,
+                        int n_boxes, void* stream);
+
+/* Same merge for a regular tile grid (T1 order: tile k = j*n_x + i at (i*stride_x, j*stride_y)),
+ * gather form, no atomics: every slide pixel takes the max over the tiles covering it. */
+ESPNET_API int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit,
+                       const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
+                       int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream);
+
+/* T4 (eval_wsi_segmentation.py:225-240): ds[y,x] = level0[ysrc[y], xsrc[x]] (or 0 where the LUT is <0).
+ * The LUTs are computed on the host in double (espnet_ds8_lut) so that cv2's INTER_NEAREST index
+ * is reproduced bit-exactly. */
+ESPNET_API int espnet_ds8_lut(int slide_len, int ws, int limit, int32_t* lut_host, int lut_len);
+ESPNET_API int espnet_downsample_lut(const uint8_t* level0, int slide_h, int slide_w, uint8_t* ds, int ds_h, int ds_w,
+                          const int32_t* ysrc_dev, const int32_t* xsrc_dev, void* stream);
+
+/* IOUEval.py:19-21 fast_hist: hist[n*gt + pred] += 1 for gt in [0,n) ; hist is int64[n*n] on device (added to). */
+ESPNET_API int espnet_confusion_hist(const uint8_t* pred, const uint8_t* gt, size_t count, int n_classes,
+                          unsigned long long* hist_dev, void* stream);
+
+/* counters for the bench: number of kernel launches issued by this library since process start */
+ESPNET_API unsigned long long espnet_launch_count(void);
+ESPNET_API int espnet_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESPNET_B200_H_ */

@@ -34,3 +34,16 @@ def fold_sd():
             cache[fold] = load_fold_state_dict(fold)
         return cache[fold]
     return get
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The CUDA library is compiled in-tree (nvcc cross-compiles without a GPU); tests never run against a
+    missing or stale build silently."""
+    from glomeruli_segmentation_b200 import _lib
+    src_dir = os.path.join(ROOT, "glomeruli_segmentation_b200", "csrc")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".sh"))]
+    srcs.append(os.path.join(ROOT, "include", "espnet_b200.h"))
+    if (not os.path.isfile(_lib.LIB_PATH)) or os.path.getmtime(_lib.LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
+        _lib.build()
+    return _lib.LIB_PATH

@@ -1,0 +1,240 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the drop-in modules
+and therefore through the C ABI, against the golden fixtures generated from the real reference and
+against the CPU oracle on the same seeded inputs.  Tolerances: fp32 logits <= 1e-3 max-abs (north_star);
+integer / index work bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from glomeruli_segmentation_b200 import ESPNet, ESPNet_Encoder, ESPNetEnsemble, FOLD_MEAN_STD, iouEval, wsi
+from oracle import espnet_oracle as O
+from oracle import wsi_oracle as W
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-3       # north_star: fp32 logits within 1e-3 max-abs
+DEV = "cuda:0"
+
+
+def _model(sd, classes=5, p=2, q=8):
+    m = ESPNet(classes, p, q)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval()
+
+
+def _maxabs(a, b):
+    return (torch.as_tensor(a).float().cpu() - torch.as_tensor(b).float().cpu()).abs().max().item()
+
+
+@pytest.mark.parametrize("fold", [1, 3])
+def test_logits_and_masks_match_reference_golden(golden, fold_sd, fold):
+    m = _model(fold_sd(fold))
+    x = torch.from_numpy(golden["small_x_fold%d" % fold]).to(DEV)
+    y = m(x)
+    assert y.shape == (3, 5, 64, 96) and y.dtype == torch.float32
+    assert _maxabs(y, golden["small_logits_fold%d" % fold]) <= LOGIT_TOL
+    mask = y.max(1)[1].byte().cpu().numpy()
+    assert (mask == golden["small_mask_fold%d" % fold]).mean() >= 0.9999
+
+
+def test_u8_path_is_bit_identical_to_f32_path(golden, fold_sd):
+    """P0 fused into the stem: the normalisation must be bit-exact, so both input formats give identical logits."""
+    m = _model(fold_sd(1))
+    mean, std = FOLD_MEAN_STD[1]
+    y32 = m(torch.from_numpy(golden["small_x_fold1"]).to(DEV))
+    u8 = torch.from_numpy(golden["small_u8"]).to(DEV)
+    lg = torch.empty_like(y32)
+    mask = m.segment(u8, mean, std, logits=lg)
+    assert torch.equal(lg, y32)
+    assert torch.equal(mask, y32.max(1)[1].byte())
+    assert (mask.cpu().numpy() == golden["small_mask_fold1"]).mean() >= 0.9999
+    host = m.segment_host(golden["small_u8"], mean, std)
+    assert np.array_equal(host, mask.cpu().numpy())
+
+
+def test_mid_crop_stages_against_oracle_and_golden(golden, fold_sd):
+    sd = fold_sd(1)
+    m = _model(sd)
+    mean, std = FOLD_MEAN_STD[1]
+    xn = O.normalise_bgr_u8(golden["mid_u8"], mean, std)
+    y = m(torch.from_numpy(xn).to(DEV))
+    taps = {}
+    ref = O.espnet_forward(sd, torch.from_numpy(xn), taps)
+    for stage, tap in [("b1", "b1"), ("b2", "b2"), ("b3", "b3"), ("up_l3", "up_l3"), ("up_l2", "up_l2")]:
+        got = m.read_stage(stage).cpu().reshape(taps[tap].shape)
+        assert _maxabs(got, taps[tap]) <= 2e-4, stage
+    assert _maxabs(y, ref) <= LOGIT_TOL
+    assert _maxabs(y, golden["mid_logits_fold1"]) <= LOGIT_TOL
+    assert _maxabs(m.read_stage("b3").cpu().reshape(1, 256, 24, 32), golden["mid_tap:encoder.b3"].astype(np.float32)) <= 3e-2
+    assert (y.max(1)[1].byte().cpu().numpy() == golden["mid_mask_fold1"]).mean() >= 0.9999
+
+
+def test_encoder_only_and_upsampled_mask(golden, fold_sd):
+    sd = O.encoder_state_dict(fold_sd(1))
+    e = ESPNet_Encoder(5, 2, 8)
+    e.load_state_dict(sd, strict=True)
+    e = e.to(DEV).eval()
+    mean, std = FOLD_MEAN_STD[1]
+    xn = torch.from_numpy(O.normalise_bgr_u8(golden["mid_u8"], mean, std)).to(DEV)
+    y = e(xn)
+    assert y.shape == (1, 5, 24, 32)
+    assert _maxabs(y, golden["mid_enc_logits_fold1"]) <= LOGIT_TOL
+    mask = e.segment_upsampled(torch.from_numpy(golden["mid_u8"]).to(DEV), mean, std)
+    assert (mask.cpu().numpy() == golden["mid_enc_mask_fold1"]).mean() >= 0.9995
+
+
+def test_five_fold_softmax_ensemble(golden, fold_sd):
+    models = [_model(fold_sd(k)) for k in range(1, 6)]
+    ens = ESPNetEnsemble(models, [FOLD_MEAN_STD[k] for k in range(1, 6)])
+    mask, prob = ens.segment(torch.from_numpy(golden["ens_u8"]).to(DEV), return_prob=True)
+    assert _maxabs(prob, golden["ens_prob"]) <= 1e-4
+    assert (mask.cpu().numpy() == golden["ens_mask"]).mean() >= 0.9995
+
+
+@pytest.mark.parametrize("classes,p,q,B,H,W", [(5, 1, 1, 2, 8, 8), (5, 3, 2, 3, 16, 24), (5, 2, 3, 2, 72, 40),
+                                               (20, 2, 3, 1, 40, 136), (5, 2, 8, 1, 264, 328)])
+def test_random_weights_and_ragged_shapes_against_oracle(classes, p, q, B, H, W):
+    sd = O.random_state_dict(classes, p, q, seed=100 + H)
+    m = _model(sd, classes, p, q)
+    x = torch.from_numpy(O.normalise_bgr_u8(O.synth_crops("D1", B, H, W, seed=H + W), *FOLD_MEAN_STD[2]))
+    ref = O.espnet_forward(sd, x)
+    y = m(x.to(DEV))
+    assert y.shape == ref.shape
+    assert _maxabs(y, ref) <= LOGIT_TOL * max(1.0, ref.abs().max().item() / 10.0)
+    esd = O.encoder_state_dict(sd)
+    e = ESPNet_Encoder(classes, p, q)
+    e.load_state_dict(esd)
+    e = e.to(DEV).eval()
+    assert _maxabs(e(x.to(DEV)), O.espnet_encoder_forward(esd, x)) <= LOGIT_TOL
+
+
+def test_full_size_crop_against_oracle_and_batch_invariance(fold_sd):
+    sd = fold_sd(3)
+    m = _model(sd)
+    mean, std = FOLD_MEAN_STD[3]
+    u8 = np.concatenate([O.synth_crops("D1", 1, 512, 512, seed=1), O.synth_crops("D2", 2, 512, 512, seed=2, sigma=8.0)])
+    ref = O.espnet_forward(sd, torch.from_numpy(O.normalise_bgr_u8(u8[:2], mean, std)))
+    d = torch.from_numpy(u8).to(DEV)
+    lg = torch.empty((3, 5, 512, 512), device=DEV)
+    mask = m.segment(d, mean, std, logits=lg)
+    assert _maxabs(lg[:2], ref) <= LOGIT_TOL
+    assert (mask[:2].cpu().numpy() == O.argmax_mask(ref)).mean() >= 0.9999
+    # size-independent properties at the full size: a crop's result does not depend on its batch, and
+    # two runs are bit-identical (no atomics / no order dependence in the forward)
+    big = d.repeat(22, 1, 1, 1)[:64]
+    mb = m.segment(big, mean, std)
+    assert torch.equal(mb[0], mask[0]) and torch.equal(mb[3 * 21], mask[0]) and torch.equal(mb[62], mask[62 % 3])
+    assert torch.equal(m.segment(big, mean, std), mb)
+
+
+def test_error_behaviour(fold_sd):
+    m = _model(fold_sd(1))
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        m(torch.zeros(1, 3, 20, 16, device=DEV))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 16, 16))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 16, 16, device=DEV))
+    m.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(torch.zeros(1, 3, 16, 16, device=DEV))
+    m.eval()
+    # editing weights + repack is honoured (no stale packed copy)
+    x = torch.randn(1, 3, 16, 16, device=DEV) * 0.01
+    y0 = m(x)
+    sd = {k: v.clone() for k, v in fold_sd(1).items()}
+    sd["classifier.weight"] = sd["classifier.weight"] * 2.0
+    m.load_state_dict(sd)
+    assert _maxabs(m(x), 2.0 * y0) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------- WSI
+def _synth_slide(h, w, seed):
+    rng = np.random.default_rng(seed)
+    coarse = rng.integers(60, 256, (h // 16 + 2, w // 16 + 2, 3)).astype(np.float32)
+    up = np.kron(coarse, np.ones((16, 16, 1), np.float32))[:h, :w]
+    return np.clip(up + rng.normal(0, 12, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def test_tiles_read_from_resident_slide_match_cut_tiles(fold_sd):
+    m = _model(fold_sd(1))
+    mean, std = FOLD_MEAN_STD[1]
+    slide = _synth_slide(300, 420, 7)
+    grid = wsi.tile_grid(420, 300, 96, 1.0, 1.0, 0.25, 1.0)      # last row / column overhang the slide
+    org = grid.origins()
+    cut = np.stack([W.read_tile(slide, int(x0), int(y0), grid.win_x, grid.win_y) for x0, y0 in org])
+    a = m.segment(torch.from_numpy(cut).to(DEV), mean, std)
+    b = m.segment_tiles(torch.from_numpy(slide).to(DEV), torch.from_numpy(org).to(DEV), grid.win_y, grid.win_x, mean, std)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("sw,sh,ws", [(1000, 760, 240), (500, 1300, 160), (333, 257, 80)])
+def test_stitch_boxes_bit_exact(sw, sh, ws):
+    rng = np.random.default_rng(sw)
+    boxes, masks = [], []
+    for _ in range(60):
+        x0, y0 = int(rng.integers(-40, sw - 5)), int(rng.integers(-40, sh - 5))
+        w, h = int(rng.integers(3, 220)), int(rng.integers(3, 220))
+        boxes.append([float(x0), float(y0), float(x0 + w), float(y0 + h), 0.9])
+        masks.append(rng.integers(0, 5, (h, w)).astype(np.uint8))
+    level0, ds8 = W.stitch_slide(boxes, masks, sw, sh, ws)
+    got = torch.zeros((sh, sw), dtype=torch.uint8, device=DEV)
+    wsi.stitch_boxes(got, boxes, [torch.from_numpy(m).to(DEV) for m in masks], ws)
+    assert np.array_equal(got.cpu().numpy(), level0)
+    assert np.array_equal(wsi.downsample8(got, ws).cpu().numpy(), ds8)
+
+
+@pytest.mark.parametrize("sw,sh,ov", [(1000, 760, 0.1), (640, 900, 0.5), (515, 389, 0.3)])
+def test_stitch_grid_bit_exact_and_band_sharding(sw, sh, ov):
+    ws = 80
+    grid = wsi.tile_grid(sw, sh, 96, 1.0, 1.0, ov, 1.0)
+    rng = np.random.default_rng(sh)
+    tiles = rng.integers(0, 5, (grid.count, grid.win_y, grid.win_x)).astype(np.uint8)
+    org = grid.origins()
+    boxes = [[float(x), float(y), float(x + grid.win_x), float(y + grid.win_y), 1.0] for x, y in org]
+    level0, ds8 = W.stitch_slide(boxes, list(tiles), sw, sh, ws)
+    d_tiles = torch.from_numpy(tiles).to(DEV)
+    full = torch.zeros((sh, sw), dtype=torch.uint8, device=DEV)
+    wsi.stitch_grid(full, d_tiles, grid, 0, grid.n_y, ws)
+    assert np.array_equal(full.cpu().numpy(), level0)
+    assert np.array_equal(wsi.downsample8(full, ws).cpu().numpy(), ds8)
+    # 3 "ranks": per-band stitch + element-wise max == the single pass (what the NCCL max-reduce does)
+    acc = torch.zeros_like(full)
+    for r in range(3):
+        r0, rows = wsi.shard_rows(grid.n_y, r, 3)
+        part = torch.zeros_like(full)
+        wsi.stitch_grid(part, d_tiles[r0 * grid.n_x:(r0 + rows) * grid.n_x], grid, r0, rows, ws)
+        acc = torch.maximum(acc, part)
+    assert torch.equal(acc, full)
+
+
+def test_small_slide_end_to_end_against_oracle_composition(fold_sd):
+    """Config 4 in miniature: T1 tiles -> forward -> arg-max -> T3 -> T4, oracle = same composition on CPU."""
+    sd = fold_sd(1)
+    m = _model(sd)
+    mean, std = FOLD_MEAN_STD[1]
+    sh, sw, ws = 264, 392, 80
+    slide = _synth_slide(sh, sw, 3)
+    o, nx, ny, wx, wy, sx, sy = W.tile_grid(sw, sh, 128, 1.0, 1.0, 0.25, 1.0)
+    cut = np.stack([W.read_tile(slide, int(x0), int(y0), wx, wy) for x0, y0 in o])
+    ref_masks = O.argmax_mask(O.espnet_forward(sd, torch.from_numpy(O.normalise_bgr_u8(cut, mean, std))))
+    boxes = [[float(x), float(y), float(x + wx), float(y + wy), 1.0] for x, y in o]
+    ref0, ref8 = W.stitch_slide(boxes, list(ref_masks), sw, sh, ws)
+    lvl0, ds8, n = wsi.segment_slide(m, torch.from_numpy(slide).to(DEV), mean, std, std_size=128, overlap=0.25, ws=ws, batch=5)
+    assert n == nx * ny
+    assert (lvl0.cpu().numpy() == ref0).mean() >= 0.9999
+    assert (ds8.cpu().numpy() == ref8).mean() >= 0.9995
+
+
+def test_gpu_confusion_histogram_matches_reference_ioueval():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "iou_golden.npz"))
+    ev = iouEval(5)
+    for i in range(3):
+        ev.addBatch(torch.from_numpy(z["pred"][i].astype(np.uint8)).to(DEV), torch.from_numpy(z["gt"][i].astype(np.uint8)).to(DEV))
+    assert np.array_equal(ev.hist, z["hist"])
+    overall, per_acc, per_iou, miou = ev.getMetricRight()
+    assert np.allclose(per_iou, z["per_iou"]) and np.isclose(miou, z["miou"])
+    big_p = torch.randint(0, 5, (3_000_000,), dtype=torch.uint8, device=DEV)
+    big_g = torch.randint(0, 5, (3_000_000,), dtype=torch.uint8, device=DEV)
+    ev2 = iouEval(5)
+    assert np.array_equal(ev2.addBatch(big_p, big_g), W.fast_hist(big_g.cpu().numpy(), big_p.cpu().numpy(), 5))
