@@ -131,6 +131,7 @@ class _Engine:
         self.handle = None
         self.device_index = None
         self.mode = _lib.MODE_FP32
+        self.options = {}
         self._ws = None
 
     def close(self):
@@ -158,6 +159,8 @@ class _Engine:
                 raise RuntimeError("espnet_create failed (code %d): %s" % (rc, _lib.last_error(None)))
             self.handle, self.device_index, self._ws = h, idx, None
             _lib.check(_lib.lib().espnet_set_mode(self.handle, self.mode), self.handle, "espnet_set_mode")
+            for k, v in self.options.items():
+                _lib.check(_lib.lib().espnet_set_option(self.handle, k.encode(), v), self.handle, "espnet_set_option")
         return self.handle
 
     def pack(self, state: Dict[str, torch.Tensor]):
@@ -231,6 +234,13 @@ class _KernelBacked(nn.Module):
         self._engine.mode = {"fp32": _lib.MODE_FP32, "f16tc": _lib.MODE_F16TC}[mode]
         if self._engine.handle is not None:
             _lib.check(_lib.lib().espnet_set_mode(self._engine.handle, self._engine.mode), self._engine.handle, "espnet_set_mode")
+        return self
+
+    def set_option(self, key: str, value: int):
+        """Library tuning knob (espnet_set_option), e.g. set_option('branch_impl', 2) forces the TMA-staged kernel."""
+        self._engine.options[key] = int(value)
+        if self._engine.handle is not None:
+            _lib.check(_lib.lib().espnet_set_option(self._engine.handle, key.encode(), int(value)), self._engine.handle, "espnet_set_option")
         return self
 
     def _own_state(self) -> Dict[str, torch.Tensor]:

@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libespnet_b200.so")
+# ESPNET_B200_LIB: developer override used to A/B kernel variants; the default is the in-tree build
+LIB_PATH = os.environ.get("ESPNET_B200_LIB") or os.path.join(_HERE, "csrc", "libespnet_b200.so")
 
 OK, EINVAL, ESHAPE, ECUDA, ESTATE, EMISSING = 0, -1, -2, -3, -4, -5
 IN_F32_NCHW, IN_U8_BGR_HWC, IN_U8_SLIDE = 0, 1, 2
@@ -37,6 +38,7 @@ SYMBOLS = {
     "espnet_last_error": (C.c_char_p, [C.c_void_p]),
     "espnet_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(TensorDesc), C.c_int]),
     "espnet_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "espnet_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "espnet_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "espnet_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs)]),
     "espnet_read_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),

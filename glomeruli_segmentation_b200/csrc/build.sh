@@ -5,4 +5,4 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
       -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared \
-      -o libespnet_b200.so espnet_api.cu "$@"
+      -o "${OUT:-libespnet_b200.so}" espnet_api.cu "$@"

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernels_fp32.cuh"
+#include "kernels_fp32_tma.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_wsi.cuh"
 
@@ -77,6 +78,7 @@ struct espnet_handle {
     size_t nparams = 0;
     Packed pk;
     std::map<std::string, StageRef> stages;
+    int branch_impl = 0;   // 0 auto, 1 per-thread global loads, 2 TMA-staged (espnet_set_option "branch_impl")
     // per-kernel CUDA-event timing (espnet_set_profiling)
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t e0, e1; };
@@ -230,7 +232,10 @@ Workspace layout(const espnet_t* h, int B, int H, int W) {
     auto take = [&](size_t elems) { const size_t o = off; off = align_up(off + elems, 64); return o; };
     w.inp1raw = take((size_t)B * 3 * P2);
     w.out0cat = take((size_t)B * 19 * P2);
-    w.o1 = take((size_t)B * 12 * P4 > (size_t)B * 25 * P8 ? (size_t)B * 12 * P4 : (size_t)B * 25 * P8);
+    {   // o1 rows are padded to a multiple of 4 floats so that the map can be a TMA tensor (16 B strides)
+        const size_t p4 = (size_t)(H / 4) * (size_t)pad4(W / 4), p8 = (size_t)(H / 8) * (size_t)pad4(W / 8);
+        w.o1 = take((size_t)B * 12 * p4 > (size_t)B * 25 * p8 ? (size_t)B * 12 * p4 : (size_t)B * 25 * p8);
+    }
     w.l2a = take((size_t)B * 64 * P4);
     w.l2b = take((size_t)B * 64 * P4);
     w.out1cat = take((size_t)B * 131 * P4);
@@ -259,14 +264,15 @@ int grid_for(const espnet_t* h, long long items) {
 long long tile_items(int B, int H, int W) { return (long long)B * ((H + kRows - 1) / kRows) * ((W + 31) / 32); }
 
 template <int CIN, int CO>
-int run_reduce1x1(espnet_t* h, const float* in, size_t w_off, float* o1, int B, int HW, cudaStream_t st) {
+int run_reduce1x1(espnet_t* h, const float* in, size_t w_off, float* o1, int B, int H, int W, cudaStream_t st) {
+    const int HW = H * W;
     const size_t smem = (size_t)CIN * pad4(CO) * sizeof(float);
     const long long items = (long long)B * ((HW + 127) / 128);
     const int threads = 256;
     long long ctas = (items + 7) / 8;
     const long long cap = 2LL * h->num_sms;
     if (ctas > cap) ctas = cap;
-    { ProfScope _ps(h, CIN == 64 ? "reduce1x1_l2" : "reduce1x1_l3", st); reduce1x1_kernel<CIN, CO><<<(int)ctas, threads, smem, st>>>(in, h->dparams + w_off, o1, B, HW); }
+    { ProfScope _ps(h, CIN == 64 ? "reduce1x1_l2" : "reduce1x1_l3", st); reduce1x1_kernel<CIN, CO><<<(int)ctas, threads, smem, st>>>(in, h->dparams + w_off, o1, B, HW, W, pad4(W)); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -274,13 +280,44 @@ int run_reduce1x1(espnet_t* h, const float* in, size_t w_off, float* o1, int B, 
 
 template <int CIN, int CO>
 int run_reduce3x3(espnet_t* h, const float* in, size_t w_off, float* o1, int B, int Hi, int Wi, cudaStream_t st) {
-    const size_t smem = (size_t)9 * CIN * pad4(CO) * sizeof(float);
+    const size_t smem = ((size_t)9 * CIN + 4) * pad4(CO) * sizeof(float);
     int rc = set_smem(h, reduce3x3s2_kernel<CIN, CO>, smem);
     if (rc) return rc;
     const int grid = grid_for(h, tile_items(B, Hi / 2, Wi / 2));
-    { ProfScope _ps(h, CIN == 19 ? "reduce3x3s2_l2" : "reduce3x3s2_l3", st); reduce3x3s2_kernel<CIN, CO><<<grid, 384, smem, st>>>(in, h->dparams + w_off, o1, B, Hi, Wi); }
+    { ProfScope _ps(h, CIN == 19 ? "reduce3x3s2_l2" : "reduce3x3s2_l3", st); reduce3x3s2_kernel<CIN, CO><<<grid, kHeavyThreads, smem, st>>>(in, h->dparams + w_off, o1, B, Hi, Wi, pad4(Wi / 2)); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// fp32 tensor map over o1 [B][N][H][Wp] with a [1][CH][64][64] box, zero OOB fill, no swizzle
+int make_o1_map(espnet_t* h, CUtensorMap* map, const float* o1, int B, int N, int H, int W, int Wp, int CH) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Wp * 4, (cuuint64_t)H * Wp * 4, (cuuint64_t)N * H * Wp * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kTmaBox, (cuuint32_t)kTmaBox, (cuuint32_t)CH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)o1, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return ESPNET_OK;
 }
 
@@ -288,9 +325,6 @@ template <int N, int CO1, int CO>
 int run_branch(espnet_t* h, const BlockW& bw, const float* o1, const float* res, float* out, float* out2, int C2, int c2_off,
                size_t s2, size_t t2, size_t a2, int B, int H, int W, cudaStream_t st) {
     constexpr int C = CO1 + 4 * CO;
-    const size_t smem = ((size_t)9 * N * pad4(CO1) + (size_t)36 * N * pad4(CO) + 6 * C) * sizeof(float);
-    int rc = set_smem(h, esp_branch_kernel<N, CO1, CO>, smem);
-    if (rc) return rc;
     BranchParams p{};
     p.o1 = o1;
     p.w_d1 = h->dparams + bw.d1;
@@ -300,9 +334,32 @@ int run_branch(espnet_t* h, const BlockW& bw, const float* o1, const float* res,
     p.out = out;
     p.s2 = h->dparams + s2; p.t2 = h->dparams + t2; p.a2 = h->dparams + a2;
     p.out2 = out2; p.C2 = C2; p.c2_off = c2_off;
-    p.B = B; p.H = H; p.W = W;
+    p.B = B; p.H = H; p.W = W; p.Wp = pad4(W);
+
+    const long long cta_tiles = (long long)B * ((H + kTmaTile - 1) / kTmaTile) * ((W + kTmaTile - 1) / kTmaTile);
+    // the TMA-staged kernel works on 32x32 CTA tiles: it needs about one tile per SM to fill the machine
+    const bool use_tma = h->branch_impl == 2 || (h->branch_impl == 0 && cta_tiles >= (long long)h->num_sms);
+    if (use_tma) {
+        constexpr int CH = (N == 25) ? 2 : 3;
+        constexpr int NS = 3;
+        using Cfg = BranchTmaCfg<N, CO1, CO, CH, NS>;
+        int rc = set_smem(h, esp_branch_tma_kernel<N, CO1, CO, CH, NS>, Cfg::SMEM);
+        if (rc) return rc;
+        CUtensorMap map;
+        rc = make_o1_map(h, &map, o1, B, N, H, W, p.Wp, CH);
+        if (rc) return rc;
+        const int grid = grid_for(h, cta_tiles);
+        { ProfScope _ps(h, N == 12 ? "esp_branch_l2" : "esp_branch_l3", st);
+          esp_branch_tma_kernel<N, CO1, CO, CH, NS><<<grid, 256, Cfg::SMEM, st>>>(map, p); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        return ESPNET_OK;
+    }
+    const size_t smem = ((size_t)9 * N * pad4(CO1) + (size_t)36 * N * pad4(CO) + 16 * pad4(CO1) + 6 * C) * sizeof(float);
+    int rc = set_smem(h, esp_branch_kernel<N, CO1, CO>, smem);
+    if (rc) return rc;
     const int grid = grid_for(h, tile_items(B, H, W));
-    { ProfScope _ps(h, N == 12 ? "esp_branch_l2" : "esp_branch_l3", st); esp_branch_kernel<N, CO1, CO><<<grid, 384, smem, st>>>(p); }
+    { ProfScope _ps(h, N == 12 ? "esp_branch_l2" : "esp_branch_l3", st); esp_branch_kernel<N, CO1, CO><<<grid, kHeavyThreads, smem, st>>>(p); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -452,6 +509,12 @@ int espnet_set_mode(espnet_t* h, int mode) {
     return ESPNET_OK;
 }
 
+int espnet_set_option(espnet_t* h, const char* key, int value) {
+    if (!h || !key) return ESPNET_EINVAL;
+    if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
+    return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);
+}
+
 int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n) {
     if (!h || !tensors || n <= 0) return fail(h, ESPNET_EINVAL, "espnet_pack_weights: bad arguments");
     std::map<std::string, HostTensor> sd;
@@ -583,7 +646,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
         float* nxt = ws + L.l2b;
         for (int i = 0; i < h->p; ++i) {
             const bool last = i == h->p - 1;
-            rc = run_reduce1x1<64, 12>(h, cur, pk.l2[i].c1, ws + L.o1, B, H4 * W4, st);
+            rc = run_reduce1x1<64, 12>(h, cur, pk.l2[i].c1, ws + L.o1, B, H4, W4, st);
             if (rc) return rc;
             rc = run_branch<12, 16, 12>(h, pk.l2[i], ws + L.o1, cur, last ? nullptr : nxt, last ? ws + L.out1cat : nullptr, 131, 0,
                                         pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
@@ -602,7 +665,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
         float* nxt = ws + L.l3b;
         for (int i = 0; i < h->q; ++i) {
             const bool last = i == h->q - 1;
-            rc = run_reduce1x1<128, 25>(h, cur, pk.l3[i].c1, ws + L.o1, B, H8 * W8, st);
+            rc = run_reduce1x1<128, 25>(h, cur, pk.l3[i].c1, ws + L.o1, B, H8, W8, st);
             if (rc) return rc;
             rc = run_branch<25, 28, 25>(h, pk.l3[i], ws + L.o1, cur, last ? nullptr : nxt, last ? ws + L.out2cat : nullptr, 256, 128,
                                         pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);

@@ -16,6 +16,22 @@
 namespace espnet {
 
 constexpr int kRows = 4;  // pixels (rows) per thread in the register tile
+#ifndef ESPNET_HEAVY_THREADS
+#define ESPNET_HEAVY_THREADS 256
+#endif
+#ifndef ESPNET_PIPE
+#define ESPNET_PIPE 0
+#endif
+#ifndef ESPNET_G25
+#define ESPNET_G25 5
+#endif
+#ifndef ESPNET_G12
+#define ESPNET_G12 4
+#endif
+constexpr int kHeavyThreads = ESPNET_HEAVY_THREADS;   // reduce3x3 / branch kernels, 1 CTA per SM
+
+template <int V>
+struct IntTag { static constexpr int value = V; };
 
 __device__ __forceinline__ float bn_prelu(float v, float s, float t, float a) {
     v = fmaf(v, s, t);
@@ -204,12 +220,139 @@ struct TileIter {
 };
 
 // ------------------------------------------------------------------------------------------------
+// acc += 3x3 conv (stride S, dilation d, zero padding d) of the N-channel planar map `src` for the
+// thread's 4 output pixels (rows yo0..yo0+3 at column xo).  Input channels are consumed in groups of G
+// with a register double buffer: the global loads of group i+1 (possibly the first group of the next
+// tap) are issued before the FFMAs of group i, so the L2 latency of the activation loads is covered
+// by ~4*G*CO FFMAs per warp instead of being exposed at every step.  Taps that fall into the zero
+// padding for the whole warp are dropped (warp-uniform mask).  wsm: [9][N][pad4(CO)] in shared memory
+// (+ one row of slack when N % G != 0).
+// ------------------------------------------------------------------------------------------------
+template <int N, int CO, int G, int S>
+struct Conv3x3Pipe {
+    static constexpr int CP = pad4(CO);
+    static constexpr int NG = (N + G - 1) / G;
+
+    const float* __restrict__ src;
+    size_t plane;          // input plane size in elements (Hi * pitch)
+    int Hi, Wi, pitch, Ho, Wo, yo0, xo, d;
+
+    __device__ __forceinline__ void geometry(int tap, int (&off)[kRows], bool (&ok)[kRows]) const {
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const int xi = S * xo + (kx - 1) * d;
+        const bool xok = (xo < Wo) && (xi >= 0) && (xi < Wi);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int yi = S * (yo0 + r) + (ky - 1) * d;
+            ok[r] = xok && (yo0 + r < Ho) && (yi >= 0) && (yi < Hi);
+            off[r] = ok[r] ? yi * pitch + xi : 0;
+        }
+    }
+    __device__ __forceinline__ void load(float (&a)[G][kRows], const int (&off)[kRows], const bool (&ok)[kRows], int g) const {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int ci = g * G + j;
+            const float* p = src + (size_t)ci * plane;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                bool v = ok[r];
+                if (N % G != 0) v = v && (ci < N);
+                a[j][r] = v ? __ldg(p + off[r]) : 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void fma_group(float (&acc)[kRows][CO], const float (&a)[G][kRows], const float* __restrict__ w) const {
+#pragma unroll
+        for (int j = 0; j < G; ++j) fma_tile<CO>(acc, a[j], w + j * CP);
+    }
+
+    // compiler-scheduled variant: plain tap / channel loops, loads hoisted by the unroller
+    __device__ __forceinline__ void run_simple(float (&acc)[kRows][CO], const float* __restrict__ wsm) const {
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            int off[kRows];
+            bool ok[kRows];
+            geometry(tap, off, ok);
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) any |= ok[r];
+            if (!__any_sync(0xffffffffu, any)) continue;
+            const float* wt = wsm + (size_t)tap * N * CP;
+#pragma unroll 4
+            for (int ci = 0; ci < N; ++ci) {
+                float a[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * plane + off[r]) : 0.f;
+                fma_tile<CO>(acc, a, wt + ci * CP);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void run(float (&acc)[kRows][CO], const float* __restrict__ wsm) const {
+#if ESPNET_PIPE == 0
+        run_simple(acc, wsm);
+        return;
+#endif
+        unsigned mask = 0;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            int off[kRows];
+            bool ok[kRows];
+            geometry(tap, off, ok);
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) any |= ok[r];
+            if (__any_sync(0xffffffffu, any)) mask |= 1u << tap;
+        }
+        if (mask == 0) return;
+        int tap = __ffs(mask) - 1;
+        mask &= mask - 1;
+        int off[kRows];
+        bool ok[kRows];
+        geometry(tap, off, ok);
+        float a0[G][kRows], a1[G][kRows];
+        load(a0, off, ok, 0);
+        int g = 0;
+        // two groups per trip so that the double buffer is a static ping-pong (no register copies)
+        while (true) {
+            // ---- prefetch the group after (tap,g) into a1, compute (tap,g) from a0 ----
+            int tap_n = tap, g_n = g + 1;
+            bool more = true;
+            if (g_n == NG) {
+                g_n = 0;
+                if (mask == 0) more = false;
+                else { tap_n = __ffs(mask) - 1; mask &= mask - 1; geometry(tap_n, off, ok); }
+            }
+            const float* w_cur = wsm + ((size_t)tap * N + g * G) * CP;
+            if (more) load(a1, off, ok, g_n);
+            fma_group(acc, a0, w_cur);
+            if (!more) break;
+            tap = tap_n; g = g_n;
+            // ---- same with the buffers swapped ----
+            tap_n = tap; g_n = g + 1;
+            if (g_n == NG) {
+                g_n = 0;
+                if (mask == 0) more = false;
+                else { tap_n = __ffs(mask) - 1; mask &= mask - 1; geometry(tap_n, off, ok); }
+            }
+            w_cur = wsm + ((size_t)tap * N + g * G) * CP;
+            if (more) load(a0, off, ok, g_n);
+            fma_group(acc, a1, w_cur);
+            if (!more) break;
+            tap = tap_n; g = g_n;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // ESP reduce: 1x1 conv CIN -> CO (Model.py:178,192), o1 planar [B,CO,H,W].
 // ------------------------------------------------------------------------------------------------
 template <int CIN, int CO>
 __global__ void __launch_bounds__(256) reduce1x1_kernel(const float* __restrict__ in, const float* __restrict__ w /*[CIN][pad4(CO)]*/,
-                                                        float* __restrict__ o1, int B, int HW) {
+                                                        float* __restrict__ o1, int B, int HW, int W, int Wp) {
     constexpr int CP = pad4(CO);
+    constexpr int G = 4;
+    static_assert(CIN % (2 * G) == 0, "channel groups are processed in ping-pong pairs");
     extern __shared__ __align__(16) float smem[];
     copy_to_smem(smem, w, CIN * CP);
     __syncthreads();
@@ -230,19 +373,34 @@ __global__ void __launch_bounds__(256) reduce1x1_kernel(const float* __restrict_
 #pragma unroll
             for (int j = 0; j < CO; ++j) acc[r][j] = 0.f;
         const float* src = in + (size_t)b * CIN * HW + p0;
-#pragma unroll 4
-        for (int ci = 0; ci < CIN; ++ci) {
-            float a[kRows];
+        auto load = [&](float (&a)[G][kRows], int g) {
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * HW + 32 * r) : 0.f;
-            fma_tile<CO>(acc, a, smem + ci * CP);
+            for (int j = 0; j < G; ++j)
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) a[j][r] = ok[r] ? __ldg(src + (size_t)(g * G + j) * HW + 32 * r) : 0.f;
+        };
+        float a0[G][kRows], a1[G][kRows];
+        load(a0, 0);
+#pragma unroll 1
+        for (int g = 0; g < CIN / G; g += 2) {
+            load(a1, g + 1);
+#pragma unroll
+            for (int j = 0; j < G; ++j) fma_tile<CO>(acc, a0[j], smem + (g * G + j) * CP);
+            if (g + 2 < CIN / G) load(a0, g + 2);
+#pragma unroll
+            for (int j = 0; j < G; ++j) fma_tile<CO>(acc, a1[j], smem + ((g + 1) * G + j) * CP);
         }
-        float* dst = o1 + (size_t)b * CO * HW + p0;
+        // o1 rows are padded to Wp (16 B multiple, TMA requirement): pixel p -> (p / W) * Wp + p % W
+        const size_t oplane = (size_t)(HW / W) * Wp;
+        float* dst = o1 + (size_t)b * CO * oplane;
 #pragma unroll
-        for (int j = 0; j < CO; ++j)
+        for (int r = 0; r < kRows; ++r) {
+            if (!ok[r]) continue;
+            const int pp = p0 + 32 * r;
+            const size_t o = (W == Wp) ? (size_t)pp : (size_t)(pp / W) * Wp + (pp % W);
 #pragma unroll
-            for (int r = 0; r < kRows; ++r)
-                if (ok[r]) dst[(size_t)j * HW + 32 * r] = acc[r][j];
+            for (int j = 0; j < CO; ++j) dst[(size_t)j * oplane + o] = acc[r][j];
+        }
     }
 }
 
@@ -251,14 +409,16 @@ __global__ void __launch_bounds__(256) reduce1x1_kernel(const float* __restrict_
 // -> o1 [B,CO,Hi/2,Wi/2].  Weights [tap][CIN][pad4(CO)] resident in shared memory.
 // ------------------------------------------------------------------------------------------------
 template <int CIN, int CO>
-__global__ void __launch_bounds__(384, 1) reduce3x3s2_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                             float* __restrict__ o1, int B, int Hi, int Wi) {
+__global__ void __launch_bounds__(kHeavyThreads, 1) reduce3x3s2_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                                       float* __restrict__ o1, int B, int Hi, int Wi, int Wop) {
     constexpr int CP = pad4(CO);
+    constexpr int G = 4;
     extern __shared__ __align__(16) float smem[];
     copy_to_smem(smem, w, 9 * CIN * CP);
+    for (int i = threadIdx.x; i < G * CP; i += blockDim.x) smem[9 * CIN * CP + i] = 0.f;   // slack rows read with a == 0
     __syncthreads();
     const int Ho = Hi >> 1, Wo = Wi >> 1;
-    const size_t iplane = (size_t)Hi * Wi, oplane = (size_t)Ho * Wo;
+    const size_t iplane = (size_t)Hi * Wi, oplane = (size_t)Ho * Wop;   // o1 rows are padded to a 16 B multiple (TMA)
     const TileIter it(B, Ho, Wo);
     const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int k = warp;; k += nwarp) {
@@ -271,36 +431,15 @@ __global__ void __launch_bounds__(384, 1) reduce3x3s2_kernel(const float* __rest
         for (int r = 0; r < kRows; ++r)
 #pragma unroll
             for (int j = 0; j < CO; ++j) acc[r][j] = 0.f;
-        const float* src = in + (size_t)b * CIN * iplane;
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3, kx = tap - 3 * ky;
-            const int xi = 2 * x - 1 + kx;
-            const bool xok = (x < Wo) && (xi >= 0) && (xi < Wi);
-            int off[kRows];
-            bool ok[kRows];
-#pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                const int yi = 2 * (y0 + r) - 1 + ky;
-                ok[r] = xok && (y0 + r < Ho) && (yi >= 0) && (yi < Hi);
-                off[r] = ok[r] ? yi * Wi + xi : 0;
-            }
-            const float* wt = smem + tap * CIN * CP;
-#pragma unroll 4
-            for (int ci = 0; ci < CIN; ++ci) {
-                float a[kRows];
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * iplane + off[r]) : 0.f;
-                fma_tile<CO>(acc, a, wt + ci * CP);
-            }
-        }
+        Conv3x3Pipe<CIN, CO, G, 2> pipe{in + (size_t)b * CIN * iplane, iplane, Hi, Wi, Wi, Ho, Wo, y0, x, 1};
+        pipe.run(acc, smem);
         if (x < Wo) {
-            float* dst = o1 + (size_t)b * CO * oplane + (size_t)y0 * Wo + x;
+            float* dst = o1 + (size_t)b * CO * oplane + (size_t)y0 * Wop + x;
 #pragma unroll
             for (int j = 0; j < CO; ++j)
 #pragma unroll
                 for (int r = 0; r < kRows; ++r)
-                    if (y0 + r < Ho) dst[(size_t)j * oplane + (size_t)r * Wo] = acc[r][j];
+                    if (y0 + r < Ho) dst[(size_t)j * oplane + (size_t)r * Wop] = acc[r][j];
         }
     }
 }
@@ -325,19 +464,25 @@ struct BranchParams {
     float* out2;            // [B,C2,H,W] or nullptr
     int C2, c2_off;
     int B, H, W;
+    int Wp;                 // row pitch of o1 (W rounded up to 4 floats)
 };
 
 template <int N, int CO1, int CO>
-__global__ void __launch_bounds__(384, 1) esp_branch_kernel(const BranchParams p) {
+__global__ void __launch_bounds__(kHeavyThreads, 1) esp_branch_kernel(const BranchParams p) {
     constexpr int C = CO1 + 4 * CO;
     constexpr int CP1 = pad4(CO1), CP = pad4(CO);
     constexpr int W1 = 9 * N * CP1, WC = 4 * 9 * N * CP;
+    constexpr int G = (N == 25) ? ESPNET_G25 : ESPNET_G12;
     extern __shared__ __align__(16) float smem[];
+    // layout: d1 weights | slack | chain weights | slack | epilogue params.  The slack rows are read (times
+    // a == 0) by the last, partial channel group when N % G != 0.
+    constexpr int SLACK = 8 * CP1;
     float* sw1 = smem;
-    float* swc = smem + W1;
-    float* sep = swc + WC;   // 6*C epilogue params
+    float* swc = smem + W1 + SLACK;
+    float* sep = swc + WC + SLACK;   // 6*C epilogue params
     copy_to_smem(sw1, p.w_d1, W1);
     copy_to_smem(swc, p.w_chain, WC);
+    for (int i = threadIdx.x; i < SLACK; i += blockDim.x) { sw1[W1 + i] = 0.f; swc[WC + i] = 0.f; }
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         sep[i] = p.s[i]; sep[C + i] = p.t[i]; sep[2 * C + i] = p.a[i];
         if (p.out2) {
@@ -349,14 +494,55 @@ __global__ void __launch_bounds__(384, 1) esp_branch_kernel(const BranchParams p
     const size_t plane = (size_t)H * W;
     const TileIter it(p.B, H, W);
     const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float* __restrict__ res = p.res;
+    float* __restrict__ out = p.out;
+    float* __restrict__ out2 = p.out2;
 
     for (int k = warp;; k += nwarp) {
         const int item = k * gridDim.x + blockIdx.x;
         if (item >= it.total) break;
         int b, y0, x;
         it.decode(item, b, y0, x);
-        const float* src = p.o1 + (size_t)b * N * plane;
+        const size_t iplane = (size_t)H * p.Wp;
+        const float* src = p.o1 + (size_t)b * N * iplane;
         const size_t pix0 = (size_t)y0 * W + x;
+
+        // one concat slice [ch0, ch0+CNT): residual add before BN (Model.py:211-212), BN + PReLU, optional 2nd BR.
+        // The residual loads of 8 channels x 4 rows are issued together before any of them is consumed, so the
+        // epilogue pays one memory latency per 32 elements instead of one per element.
+        auto emit = [&](auto& acc, int ch0, auto cnt_tag) {
+            constexpr int CNT = decltype(cnt_tag)::value;
+            constexpr int CH = 8;
+            if (x >= W) return;
+#pragma unroll
+            for (int j0 = 0; j0 < CNT; j0 += CH) {
+                float rv[CH][kRows];
+#pragma unroll
+                for (int jj = 0; jj < CH; ++jj)
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        rv[jj][r] = 0.f;
+                        if (j0 + jj < CNT && res != nullptr && y0 + r < H)
+                            rv[jj][r] = __ldg(res + ((size_t)b * C + ch0 + j0 + jj) * plane + pix0 + (size_t)r * W);
+                    }
+#pragma unroll
+                for (int jj = 0; jj < CH; ++jj) {
+                    if (j0 + jj >= CNT) continue;
+                    const int ch = ch0 + j0 + jj;
+                    const float s1 = sep[ch], t1 = sep[C + ch], a1 = sep[2 * C + ch];
+                    float s2 = 0.f, t2 = 0.f, a2 = 0.f;
+                    if (out2 != nullptr) { s2 = sep[3 * C + ch]; t2 = sep[4 * C + ch]; a2 = sep[5 * C + ch]; }
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        if (y0 + r >= H) continue;
+                        const float v = bn_prelu(acc[r][j0 + jj] + rv[jj][r], s1, t1, a1);
+                        if (out != nullptr) out[((size_t)b * C + ch) * plane + pix0 + (size_t)r * W] = v;
+                        if (out2 != nullptr)
+                            out2[((size_t)b * p.C2 + p.c2_off + ch) * plane + pix0 + (size_t)r * W] = bn_prelu(v, s2, t2, a2);
+                    }
+                }
+            }
+        };
 
         // ---- branch d1: CO1 outputs ---------------------------------------------------------------
         {
@@ -365,44 +551,9 @@ __global__ void __launch_bounds__(384, 1) esp_branch_kernel(const BranchParams p
             for (int r = 0; r < kRows; ++r)
 #pragma unroll
                 for (int j = 0; j < CO1; ++j) acc[r][j] = 0.f;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-                const int ky = tap / 3, kx = tap - 3 * ky;
-                const int xi = x + (kx - 1);
-                const bool xok = (x < W) && (xi >= 0) && (xi < W);
-                int off[kRows];
-                bool ok[kRows];
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) {
-                    const int yi = y0 + r + (ky - 1);
-                    ok[r] = xok && (yi >= 0) && (yi < H);
-                    off[r] = ok[r] ? yi * W + xi : 0;
-                }
-                const float* wt = sw1 + tap * N * CP1;
-#pragma unroll 4
-                for (int ci = 0; ci < N; ++ci) {
-                    float a[kRows];
-#pragma unroll
-                    for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * plane + off[r]) : 0.f;
-                    fma_tile<CO1>(acc, a, wt + ci * CP1);
-                }
-            }
-            if (x < W) {
-#pragma unroll
-                for (int j = 0; j < CO1; ++j)
-#pragma unroll
-                    for (int r = 0; r < kRows; ++r) {
-                        if (y0 + r >= H) continue;
-                        const size_t o = ((size_t)b * C + j) * plane + pix0 + (size_t)r * W;
-                        float v = acc[r][j];
-                        if (p.res) v += __ldg(p.res + o);
-                        v = bn_prelu(v, sep[j], sep[C + j], sep[2 * C + j]);
-                        if (p.out) p.out[o] = v;
-                        if (p.out2)
-                            p.out2[((size_t)b * p.C2 + p.c2_off + j) * plane + pix0 + (size_t)r * W] =
-                                bn_prelu(v, sep[3 * C + j], sep[4 * C + j], sep[5 * C + j]);
-                    }
-            }
+            Conv3x3Pipe<N, CO1, G, 1> pipe{src, iplane, H, W, p.Wp, H, W, y0, x, 1};
+            pipe.run(acc, sw1);
+            emit(acc, 0, IntTag<CO1>());
         }
         // ---- chain d2 -> d4 -> d8 -> d16 with the HFF sum living in the accumulator -----------------
         {
@@ -413,50 +564,9 @@ __global__ void __launch_bounds__(384, 1) esp_branch_kernel(const BranchParams p
                 for (int j = 0; j < CO; ++j) acc[r][j] = 0.f;
 #pragma unroll 1
             for (int br = 0; br < 4; ++br) {
-                const int d = 2 << br;
-#pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int ky = tap / 3, kx = tap - 3 * ky;
-                    const int xi = x + (kx - 1) * d;
-                    const bool xok = (x < W) && (xi >= 0) && (xi < W);
-                    int off[kRows];
-                    bool ok[kRows];
-                    bool any = false;
-#pragma unroll
-                    for (int r = 0; r < kRows; ++r) {
-                        const int yi = y0 + r + (ky - 1) * d;
-                        ok[r] = xok && (yi >= 0) && (yi < H);
-                        off[r] = ok[r] ? yi * W + xi : 0;
-                        any |= ok[r];
-                    }
-                    if (!__any_sync(0xffffffffu, any)) continue;   // whole warp's tap lies in the zero padding
-                    const float* wt = swc + (br * 9 + tap) * N * CP;
-#pragma unroll 4
-                    for (int ci = 0; ci < N; ++ci) {
-                        float a[kRows];
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) a[r] = ok[r] ? __ldg(src + (size_t)ci * plane + off[r]) : 0.f;
-                        fma_tile<CO>(acc, a, wt + ci * CP);
-                    }
-                }
-                if (x < W) {
-                    const int ch0 = CO1 + br * CO;
-#pragma unroll
-                    for (int j = 0; j < CO; ++j)
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) {
-                            if (y0 + r >= H) continue;
-                            const int ch = ch0 + j;
-                            const size_t o = ((size_t)b * C + ch) * plane + pix0 + (size_t)r * W;
-                            float v = acc[r][j];
-                            if (p.res) v += __ldg(p.res + o);
-                            v = bn_prelu(v, sep[ch], sep[C + ch], sep[2 * C + ch]);
-                            if (p.out) p.out[o] = v;
-                            if (p.out2)
-                                p.out2[((size_t)b * p.C2 + p.c2_off + ch) * plane + pix0 + (size_t)r * W] =
-                                    bn_prelu(v, sep[3 * C + ch], sep[4 * C + ch], sep[5 * C + ch]);
-                        }
-                }
+                Conv3x3Pipe<N, CO, G, 1> pipe{src, iplane, H, W, p.Wp, H, W, y0, x, 2 << br};
+                pipe.run(acc, swc + br * 9 * N * CP);
+                emit(acc, CO1 + br * CO, IntTag<CO>());
             }
         }
     }

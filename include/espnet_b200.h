@@ -90,6 +90,9 @@ ESPNET_API const char* espnet_last_error(const espnet_t* h); /* h may be NULL: l
 ESPNET_API int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n);
 
 ESPNET_API int espnet_set_mode(espnet_t* h, int mode);            /* ESPNET_MODE_* ; default FP32 */
+/* Tuning knobs (never change results beyond fp32 re-association): "branch_impl" = 0 auto, 1 per-thread global
+ * loads, 2 TMA-staged shared-memory halo tiles. */
+ESPNET_API int espnet_set_option(espnet_t* h, const char* key, int value);
 ESPNET_API size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W);
 
 /* Replaces `img_out = model(img_variable)` (+ normalise before, arg-max after):

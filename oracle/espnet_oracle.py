@@ -256,11 +256,13 @@ def random_state_dict(classes=5, p=2, q=8, seed=0, encoder_only=False) -> Dict[s
         sd[key + ".conv.weight"] = torch.randn(co, ci, k, k, generator=g) * math.sqrt(1.0 / (ci * k * k))
 
     def bn(key, c):
-        sd[key + ".weight"] = torch.randn(c, generator=g) * 0.3 + 0.8
+        gamma = (torch.randn(c, generator=g) * 0.25 + 0.7) * torch.where(torch.rand(c, generator=g) < 0.15, -1.0, 1.0)
         sd[key + ".bias"] = torch.randn(c, generator=g) * 0.2
         sd[key + ".running_mean"] = torch.randn(c, generator=g) * 0.2
-        var = torch.rand(c, generator=g) * 0.8 + 0.05
-        var[::17] = 5.6e-45
+        var = torch.rand(c, generator=g) * 1.0 + 0.5
+        var[::17] = 5.6e-45          # dead channels of the shipped checkpoints: denormal variance ...
+        gamma[::17] = gamma[::17] * 0.02   # ... whose 1/sqrt(eps) = 31x gain is tamed by a tiny gamma
+        sd[key + ".weight"] = gamma
         sd[key + ".running_var"] = var
         sd[key + ".num_batches_tracked"] = torch.tensor(1000, dtype=torch.int64)
 
