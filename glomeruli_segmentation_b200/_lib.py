@@ -50,6 +50,7 @@ SYMBOLS = {
     "espnet_ds8_lut": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "espnet_downsample_lut": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "espnet_confusion_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
+    "espnet_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "espnet_launch_count": (C.c_ulonglong, []),
     "espnet_version": (C.c_int, []),
 }

@@ -3,6 +3,7 @@
 // No torch, no cuDNN, no CPU fallback: if a CUDA call fails the error is returned to the caller.
 #include "../../include/espnet_b200.h"
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -76,6 +77,8 @@ struct espnet_handle {
     bool packed = false;
     float* dparams = nullptr;
     size_t nparams = 0;
+    uint8_t* dparams_h = nullptr;   // fp16 tensor-core weights (BlockW::tc byte offsets)
+    size_t nparams_h = 0;
     Packed pk;
     std::map<std::string, StageRef> stages;
     int branch_impl = 0;   // 0 auto, 1 per-thread global loads, 2 TMA-staged (espnet_set_option "branch_impl")
@@ -129,6 +132,7 @@ struct ProfScope {
 // ----------------------------------------------------------------------------------------------
 struct Packer {
     std::vector<float> blob;
+    std::vector<uint16_t> blob_h;     // fp16 bits, tensor-core operand layout
     const std::map<std::string, HostTensor>* sd = nullptr;
     std::string missing;
 
@@ -216,6 +220,27 @@ struct Packer {
         }
         if (!ok) return false;
         bw.chain = add(v);
+        {   // tensor-core copy [5 branches][9 taps][NKC][NOUT][8] fp16: element (n, ci) of tap t = W[co = n][ci][t], zero padded
+            const int nkc = 2 * ((n + 15) / 16), nout = n1 <= 16 ? 16 : 32;
+            while (blob_h.size() % 64) blob_h.push_back(0);          // 128 B alignment (cp.async.bulk needs 16 B)
+            bw.tc = blob_h.size() * sizeof(uint16_t);
+            blob_h.resize(blob_h.size() + (size_t)5 * 9 * nkc * nout * 8, 0);
+            uint16_t* dst = blob_h.data() + bw.tc / sizeof(uint16_t);
+            const int dd[5] = {1, 2, 4, 8, 16};
+            for (int b = 0; b < 5; ++b) {
+                const int co_n = b == 0 ? n1 : n;
+                const HostTensor* w = get(key + ".d" + std::to_string(dd[b]) + ".conv.weight", {co_n, n, 3, 3});
+                if (!w) return false;
+                for (int t = 0; t < 9; ++t)
+                    for (int o = 0; o < co_n; ++o)
+                        for (int c = 0; c < n; ++c) {
+                            const __half hv = __float2half_rn(w->data[((size_t)o * n + c) * 9 + t]);
+                            uint16_t bits;
+                            std::memcpy(&bits, &hv, 2);
+                            dst[((((size_t)b * 9 + t) * nkc + c / 8) * nout + o) * 8 + (c % 8)] = bits;
+                        }
+            }
+        }
         const std::string bnk = down ? key + ".bn" : key + ".bn.bn";
         const std::string ak = down ? key + ".act.weight" : key + ".bn.act.weight";
         return bn(bnk, cout, bw.s, bw.t) && vec(ak, cout, bw.a);
@@ -365,6 +390,76 @@ int run_branch(espnet_t* h, const BlockW& bw, const float* o1, const float* res,
     return ESPNET_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- tcgen05 path
+// fp16 tensor map over o1h [B][NKC][H][W][8] with a {8, 48, 48, NKC, 1} box, zero OOB fill, no swizzle
+int make_o1h_map(espnet_t* h, CUtensorMap* map, const __half* o1h, int B, int NKC, int H, int W) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NKC, (cuuint64_t)B};
+    cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)NKC * H * W * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)kTcBox, (cuuint32_t)kTcBox, (cuuint32_t)NKC, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)o1h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled (o1h) failed with CUresult " + std::to_string((int)r));
+    return ESPNET_OK;
+}
+
+template <int CIN, int CO, int NKC>
+int run_reduce1x1_f16(espnet_t* h, const float* in, size_t w_off, __half* o1h, int B, int H, int W, cudaStream_t st) {
+    const int HW = H * W;
+    const size_t smem = (size_t)CIN * pad4(CO) * sizeof(float);
+    const long long items = (long long)B * ((HW + 127) / 128);
+    long long ctas = (items + 7) / 8;
+    const long long cap = 2LL * h->num_sms;
+    if (ctas > cap) ctas = cap;
+    { ProfScope _ps(h, CIN == 64 ? "reduce1x1_f16_l2" : "reduce1x1_f16_l3", st);
+      reduce1x1_f16_kernel<CIN, CO, NKC><<<(int)ctas, 256, smem, st>>>(in, h->dparams + w_off, o1h, B, HW); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+template <int CIN, int CO, int NKC>
+int run_reduce3x3_f16(espnet_t* h, const float* in, size_t w_off, __half* o1h, int B, int Hi, int Wi, cudaStream_t st) {
+    const size_t smem = ((size_t)9 * CIN + 4) * pad4(CO) * sizeof(float);
+    int rc = set_smem(h, reduce3x3s2_f16_kernel<CIN, CO, NKC>, smem);
+    if (rc) return rc;
+    const int grid = grid_for(h, tile_items(B, Hi / 2, Wi / 2));
+    { ProfScope _ps(h, CIN == 19 ? "reduce3x3s2_f16_l2" : "reduce3x3s2_f16_l3", st);
+      reduce3x3s2_f16_kernel<CIN, CO, NKC><<<grid, kHeavyThreads, smem, st>>>(in, h->dparams + w_off, o1h, B, Hi, Wi); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+template <int NKC, int NOUT, int CO1, int CO>
+int run_branch_tc(espnet_t* h, const BlockW& bw, const __half* o1h, const float* res, float* out, float* out2, int C2, int c2_off,
+                  size_t s2, size_t t2, size_t a2, int B, int H, int W, cudaStream_t st) {
+    using Cfg = BranchTcCfg<NKC, NOUT>;
+    BranchTcParams p{};
+    p.w = reinterpret_cast<const __half*>(h->dparams_h + bw.tc);
+    p.res = res;
+    p.s = h->dparams + bw.s; p.t = h->dparams + bw.t; p.a = h->dparams + bw.a;
+    p.out = out;
+    p.s2 = h->dparams + s2; p.t2 = h->dparams + t2; p.a2 = h->dparams + a2;
+    p.out2 = out2; p.C2 = C2; p.c2_off = c2_off;
+    p.B = B; p.H = H; p.W = W;
+    int rc = set_smem(h, esp_branch_tc_kernel<NKC, NOUT, CO1, CO>, Cfg::SMEM);
+    if (rc) return rc;
+    CUtensorMap map;
+    rc = make_o1h_map(h, &map, o1h, B, NKC, H, W);
+    if (rc) return rc;
+    const long long tiles = (long long)B * ((H + kTcTile - 1) / kTcTile) * ((W + kTcTile - 1) / kTcTile);
+    const int grid = grid_for(h, tiles);
+    { ProfScope _ps(h, NKC == 2 ? "esp_branch_tc_l2" : "esp_branch_tc_l3", st);
+      esp_branch_tc_kernel<NKC, NOUT, CO1, CO><<<grid, kTcThreads, Cfg::SMEM, st>>>(map, p); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
 template <int NC>
 int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, float* ws, cudaStream_t st) {
     const int B = a->B, H = a->H, W = a->W;
@@ -492,6 +587,7 @@ void espnet_destroy(espnet_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     if (h->dparams) cudaFree(h->dparams);
+    if (h->dparams_h) cudaFree(h->dparams_h);
     if (h->hb_in) cudaFree(h->hb_in);
     if (h->hb_mask) cudaFree(h->hb_mask);
     if (h->hb_ws) cudaFree(h->hb_ws);
@@ -503,8 +599,6 @@ void espnet_destroy(espnet_t* h) {
 int espnet_set_mode(espnet_t* h, int mode) {
     if (!h) return ESPNET_EINVAL;
     if (mode != ESPNET_MODE_FP32 && mode != ESPNET_MODE_F16TC) return fail(h, ESPNET_EINVAL, "espnet_set_mode: unknown mode");
-    if (mode == ESPNET_MODE_F16TC && !tc_path_available())
-        return fail(h, ESPNET_ESTATE, "espnet_set_mode: the tcgen05 fp16 path is not built into this library yet");
     h->mode = mode;
     return ESPNET_OK;
 }
@@ -572,6 +666,10 @@ int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n) {
     h->nparams = pk.blob.size();
     // synchronous copy: the host buffers belong to the caller and may go away after we return
     CUDA_TRY(h, cudaMemcpy(h->dparams, pk.blob.data(), pk.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (h->dparams_h && h->nparams_h < pk.blob_h.size() * 2) { cudaFree(h->dparams_h); h->dparams_h = nullptr; }
+    if (!h->dparams_h) CUDA_TRY(h, cudaMalloc(&h->dparams_h, pk.blob_h.size() * 2));
+    h->nparams_h = pk.blob_h.size() * 2;
+    CUDA_TRY(h, cudaMemcpy(h->dparams_h, pk.blob_h.data(), pk.blob_h.size() * 2, cudaMemcpyHostToDevice));
     h->packed = true;
     return ESPNET_OK;
 }
@@ -606,7 +704,8 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
     h->stages.clear();
 
-    if (h->mode == ESPNET_MODE_F16TC) return fail(h, ESPNET_ESTATE, "espnet_forward: tcgen05 path not available in this build");
+    const bool tcm = h->mode == ESPNET_MODE_F16TC;
+    __half* o1h = reinterpret_cast<__half*>(ws + L.o1);
 
     // ---- S1 stem -----------------------------------------------------------------------------------
     {
@@ -636,47 +735,139 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
         h->stages["b1"] = {ws + L.out0cat, (size_t)B * 19 * H2 * W2};
     }
     int rc;
+    // one DownSamplerB / ESP block = reduce + branch stage, on CUDA cores (fp32) or tensor cores (fp16 operands)
+    auto block_l2 = [&](const BlockW& bw, bool down, const float* in, float* out, float* out2, int c2_off) -> int {
+        int r;
+        if (tcm) {
+            r = down ? run_reduce3x3_f16<19, 12, 2>(h, in, bw.c1, o1h, B, H2, W2, st) : run_reduce1x1_f16<64, 12, 2>(h, in, bw.c1, o1h, B, H4, W4, st);
+            if (r) return r;
+            return run_branch_tc<2, 16, 16, 12>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
+        }
+        r = down ? run_reduce3x3<19, 12>(h, in, bw.c1, ws + L.o1, B, H2, W2, st) : run_reduce1x1<64, 12>(h, in, bw.c1, ws + L.o1, B, H4, W4, st);
+        if (r) return r;
+        return run_branch<12, 16, 12>(h, bw, ws + L.o1, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
+    };
+    auto block_l3 = [&](const BlockW& bw, bool down, const float* in, float* out, float* out2, int c2_off) -> int {
+        int r;
+        if (tcm) {
+            r = down ? run_reduce3x3_f16<131, 25, 4>(h, in, bw.c1, o1h, B, H4, W4, st) : run_reduce1x1_f16<128, 25, 4>(h, in, bw.c1, o1h, B, H8, W8, st);
+            if (r) return r;
+            return run_branch_tc<4, 32, 28, 25>(h, bw, o1h, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
+        }
+        r = down ? run_reduce3x3<131, 25>(h, in, bw.c1, ws + L.o1, B, H4, W4, st) : run_reduce1x1<128, 25>(h, in, bw.c1, ws + L.o1, B, H8, W8, st);
+        if (r) return r;
+        return run_branch<25, 28, 25>(h, bw, ws + L.o1, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
+    };
     // ---- S2/S3 level 2 -----------------------------------------------------------------------------
-    rc = run_reduce3x3<19, 12>(h, ws + L.out0cat, pk.l2_0.c1, ws + L.o1, B, H2, W2, st);
-    if (rc) return rc;
-    rc = run_branch<12, 16, 12>(h, pk.l2_0, ws + L.o1, nullptr, ws + L.l2a, ws + L.out1cat, 131, 64, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
+    rc = block_l2(pk.l2_0, true, ws + L.out0cat, ws + L.l2a, ws + L.out1cat, 64);
     if (rc) return rc;
     {
         float* cur = ws + L.l2a;
         float* nxt = ws + L.l2b;
+        std::string name_cur = "level2_0", name_nxt;
         for (int i = 0; i < h->p; ++i) {
             const bool last = i == h->p - 1;
-            rc = run_reduce1x1<64, 12>(h, cur, pk.l2[i].c1, ws + L.o1, B, H4, W4, st);
+            rc = block_l2(pk.l2[i], false, cur, last ? nullptr : nxt, last ? ws + L.out1cat : nullptr, 0);
             if (rc) return rc;
-            rc = run_branch<12, 16, 12>(h, pk.l2[i], ws + L.o1, cur, last ? nullptr : nxt, last ? ws + L.out1cat : nullptr, 131, 0,
-                                        pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
-            if (rc) return rc;
+            if (!last) name_nxt = "level2." + std::to_string(i);
             float* t = cur; cur = nxt; nxt = t;
+            std::swap(name_cur, name_nxt);
         }
+        // block outputs that survived the ping-pong (parity taps)
+        if (!name_cur.empty()) h->stages[name_cur] = {cur, (size_t)B * 64 * H4 * W4};
+        if (!name_nxt.empty()) h->stages[name_nxt] = {nxt, (size_t)B * 64 * H4 * W4};
         h->stages["b2"] = {ws + L.out1cat, (size_t)B * 131 * H4 * W4};
     }
     // ---- S5/S6 level 3 -----------------------------------------------------------------------------
-    rc = run_reduce3x3<131, 25>(h, ws + L.out1cat, pk.l3_0.c1, ws + L.o1, B, H4, W4, st);
-    if (rc) return rc;
-    rc = run_branch<25, 28, 25>(h, pk.l3_0, ws + L.o1, nullptr, ws + L.l3a, ws + L.out2cat, 256, 0, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
+    rc = block_l3(pk.l3_0, true, ws + L.out1cat, ws + L.l3a, ws + L.out2cat, 0);
     if (rc) return rc;
     {
         float* cur = ws + L.l3a;
         float* nxt = ws + L.l3b;
+        std::string name_cur = "level3_0", name_nxt;
         for (int i = 0; i < h->q; ++i) {
             const bool last = i == h->q - 1;
-            rc = run_reduce1x1<128, 25>(h, cur, pk.l3[i].c1, ws + L.o1, B, H8, W8, st);
+            rc = block_l3(pk.l3[i], false, cur, last ? nullptr : nxt, last ? ws + L.out2cat : nullptr, 128);
             if (rc) return rc;
-            rc = run_branch<25, 28, 25>(h, pk.l3[i], ws + L.o1, cur, last ? nullptr : nxt, last ? ws + L.out2cat : nullptr, 256, 128,
-                                        pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
-            if (rc) return rc;
+            if (!last) name_nxt = "level3." + std::to_string(i);
             float* t = cur; cur = nxt; nxt = t;
+            std::swap(name_cur, name_nxt);
         }
+        if (!name_cur.empty()) h->stages[name_cur] = {cur, (size_t)B * 128 * H8 * W8};
+        if (!name_nxt.empty()) h->stages[name_nxt] = {nxt, (size_t)B * 128 * H8 * W8};
         h->stages["b3"] = {ws + L.out2cat, (size_t)B * 256 * H8 * W8};
     }
     // ---- S7..S10 heads / decoder -------------------------------------------------------------------
     if (h->classes == 5) return run_tail<5>(h, a, L, ws, st);
     return run_tail<20>(h, a, L, ws, st);
+}
+
+// Hardware self-test of the tcgen05 operand convention (kernels_tc.cuh: tc_selftest_kernel): random fp16 A / B,
+// one tap shifted by (dy, dx), compared with a double-precision host reference.  Returns the max abs error.
+int espnet_tc_selftest(int device, int nkc, int nout, int dy, int dx, int use_tma, float* max_abs_err) {
+    if (!max_abs_err || (nkc != 2 && nkc != 4) || (nout != 16 && nout != 32) || dy < -16 || dy > 16 || dx < -16 || dx > 16)
+        return fail(nullptr, ESPNET_EINVAL, "espnet_tc_selftest: bad arguments");
+    DeviceGuard g(device);
+    // a small map (24 x 20) whose 48 x 48 box around the tile origin (4, 6) hangs over every edge
+    const int Hm = 24, Wm = 20, ox = 4, oy = 6;
+    std::vector<__half> amap((size_t)nkc * Hm * Wm * 8), apad((size_t)nkc * kTcBox * kTcBox * 8), bw((size_t)nkc * nout * 8);
+    std::vector<float> amap_f(amap.size()), bw_f(bw.size());
+    uint32_t seed = 12345u + (uint32_t)(nkc * 131 + nout * 17 + (dy + 16) * 37 + (dx + 16));
+    auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+    for (size_t i = 0; i < amap.size(); ++i) { amap[i] = __float2half_rn(rnd()); amap_f[i] = __half2float(amap[i]); }
+    for (size_t i = 0; i < bw.size(); ++i) { bw[i] = __float2half_rn(rnd()); bw_f[i] = __half2float(bw[i]); }
+    auto at = [&](int kc, int y, int x, int j) -> float {   // zero outside the map
+        if (y < 0 || y >= Hm || x < 0 || x >= Wm) return 0.f;
+        return amap_f[(((size_t)kc * Hm + y) * Wm + x) * 8 + j];
+    };
+    for (int kc = 0; kc < nkc; ++kc)
+        for (int r = 0; r < kTcBox; ++r)
+            for (int c = 0; c < kTcBox; ++c)
+                for (int j = 0; j < 8; ++j)
+                    apad[(((size_t)kc * kTcBox + r) * kTcBox + c) * 8 + j] = __float2half_rn(at(kc, oy - kTcHalo + r, ox - kTcHalo + c, j));
+    __half *d_map = nullptr, *d_pad = nullptr, *d_bw = nullptr;
+    float* d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_map); cudaFree(d_pad); cudaFree(d_bw); cudaFree(d_out); };
+#define ST_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(nullptr, ESPNET_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+    ST_TRY(cudaMalloc(&d_map, amap.size() * 2));
+    ST_TRY(cudaMalloc(&d_pad, apad.size() * 2));
+    ST_TRY(cudaMalloc(&d_bw, bw.size() * 2));
+    ST_TRY(cudaMalloc(&d_out, (size_t)128 * nout * 4));
+    ST_TRY(cudaMemcpy(d_map, amap.data(), amap.size() * 2, cudaMemcpyHostToDevice));
+    ST_TRY(cudaMemcpy(d_pad, apad.data(), apad.size() * 2, cudaMemcpyHostToDevice));
+    ST_TRY(cudaMemcpy(d_bw, bw.data(), bw.size() * 2, cudaMemcpyHostToDevice));
+    ST_TRY(cudaMemset(d_out, 0xFF, (size_t)128 * nout * 4));
+    CUtensorMap map;
+    int rc = make_o1h_map(nullptr, &map, d_map, 1, nkc, Hm, Wm);
+    if (rc) { cleanup(); return rc; }
+    const size_t smem = (size_t)4 * kTcPlaneBytes + 4 * 32 * 16 + 64;
+    if (nout == 32) {
+        ST_TRY(cudaFuncSetAttribute(tc_selftest_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_selftest_kernel<32><<<1, 128, smem>>>(map, d_pad, d_bw, d_out, nkc, dy, dx, use_tma, ox, oy);
+    } else {
+        ST_TRY(cudaFuncSetAttribute(tc_selftest_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_selftest_kernel<16><<<1, 128, smem>>>(map, d_pad, d_bw, d_out, nkc, dy, dx, use_tma, ox, oy);
+    }
+    LAUNCH_COUNT();
+    ST_TRY(cudaGetLastError());
+    ST_TRY(cudaDeviceSynchronize());
+    std::vector<float> out((size_t)128 * nout);
+    ST_TRY(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
+#undef ST_TRY
+    cleanup();
+    double worst = 0.0;
+    for (int l = 0; l < 128; ++l)
+        for (int n = 0; n < nout; ++n) {
+            double ref = 0.0;
+            for (int kc = 0; kc < nkc; ++kc)
+                for (int j = 0; j < 8; ++j)
+                    ref += (double)at(kc, oy + dy + l / 8, ox + dx + l % 8, j) * (double)bw_f[((size_t)kc * nout + n) * 8 + j];
+            const double got = (double)out[(size_t)l * nout + n];
+            const double e = std::isfinite(got) ? std::fabs(got - ref) : 1e30;
+            if (e > worst) worst = e;
+        }
+    *max_abs_err = (float)worst;
+    return ESPNET_OK;
 }
 
 int espnet_set_profiling(espnet_t* h, int on) {

@@ -142,6 +142,11 @@ ESPNET_API int espnet_downsample_lut(const uint8_t* level0, int slide_h, int sli
 ESPNET_API int espnet_confusion_hist(const uint8_t* pred, const uint8_t* gt, size_t count, int n_classes,
                           unsigned long long* hist_dev, void* stream);
 
+/* Hardware self-test of the tensor-core operand convention used by ESPNET_MODE_F16TC (no reference counterpart):
+ * one 128 x nout x (8*nkc) tcgen05.mma whose A window is shifted by (dy, dx) pixels inside a TMA-staged (use_tma = 1)
+ * or plainly copied (use_tma = 0) 48 x 48 activation box; *max_abs_err is measured against a host fp64 reference. */
+ESPNET_API int espnet_tc_selftest(int device, int nkc, int nout, int dy, int dx, int use_tma, float* max_abs_err);
+
 /* counters for the bench: number of kernel launches issued by this library since process start */
 ESPNET_API unsigned long long espnet_launch_count(void);
 ESPNET_API int espnet_version(void);
