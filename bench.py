@@ -169,6 +169,30 @@ def workload_config(workload, batch):
             "l2": "inputs (201 MB fp32 / 50 MB u8 per batch of 64) and activations (>2 GB) exceed the 126 MB L2; no flush needed"}
 
 
+def kernel_roofline(name, per_launch_ms, B, hbm_peak, peak_src):
+    """Algorithmic bytes / FLOPs of ONE launch of the ESP branch-stage kernels at 512x512 crops (kernel table):
+    per crop the kernel reads o1 (reduced map) and the residual and writes the block output once."""
+    P4, P8 = 128 * 128, 64 * 64
+    alg = {"esp_branch_l3": B * (25 + 128 + 128) * P8 * 4, "esp_branch_l2": B * (12 + 64 + 64) * P4 * 4,
+           # tensor-core mode: o1 is fp16 padded to 32 / 16 channels, residual and output stay fp32
+           "esp_branch_tc_l3": B * (32 * 2 + 128 * 4 + 128 * 4) * P8, "esp_branch_tc_l2": B * (16 * 2 + 64 * 4 + 64 * 4) * P4}.get(name)
+    flops = {"esp_branch_l3": B * P8 * 2 * 9 * 25 * 128, "esp_branch_l2": B * P4 * 2 * 9 * 12 * 64,
+             "esp_branch_tc_l3": B * P8 * 2 * 9 * 25 * 128, "esp_branch_tc_l2": B * P4 * 2 * 9 * 12 * 64}.get(name)
+    if alg is None:
+        return None
+    ach = alg / (per_launch_ms * 1e-3) / 1e9
+    roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg}
+    tf = flops / (per_launch_ms * 1e-3) / 1e12
+    if "_tc_" in name:
+        roof["note"] = "tcgen05 mode: the contraction runs on tensor cores, the kernel is bounded by HBM (SURVEY.md 8(d))"
+        roof["tensor"] = {"achieved_tflops_useful": tf}
+    else:
+        roof["note"] = "fp32 mode: this kernel is CUDA-core FMA bound, not HBM bound (SURVEY.md 8(d)); see fp32_fma"
+        roof["fp32_fma"] = {"achieved_tflops": tf, "peak_tflops": FP32_FMA_PEAK_TFLOPS, "frac": tf / FP32_FMA_PEAK_TFLOPS}
+    return roof
+
+
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
@@ -199,7 +223,7 @@ def run_ours(args):
         sd = load_weights(1, False)
     if sd is not None:
         model.load_state_dict(sd, strict=True)
-    model = model.to(dev).eval()
+    model = model.to(dev).eval().set_mode(args.mode)
     ens = None
     if wl == "espnet_b256_ens5":
         models = [model]
@@ -208,7 +232,7 @@ def run_ours(args):
             sdk = load_weights(k, False)
             if sdk is not None:
                 mk.load_state_dict(sdk, strict=True)
-            models.append(mk.to(dev).eval())
+            models.append(mk.to(dev).eval().set_mode(args.mode))
         ens = ESPNetEnsemble(models, [FOLD_MEAN_STD[k] for k in range(1, 6)])
 
     u8_host = torch.from_numpy(synth_u8(B, H, W, 1234 + rank)).pin_memory()
@@ -287,12 +311,40 @@ def run_ours(args):
     rep = model.profile_report()
     model.profile(False)
 
+    # second leg: the other compute mode on the same resident batch (reported beside the headline, never instead of it)
+    other = None
+    if ens is None and not args.single_mode:
+        om = "f16tc" if args.mode == "fp32" else "fp32"
+        ref_mask = model.segment(u8_dev, mean, std).clone()
+        model.set_mode(om)
+        for _ in range(3):
+            step_resident()
+        ms_o = timed(step_resident, args.steps)
+        model.profile(True)
+        for _ in range(prof_steps):
+            step_resident()
+        torch.cuda.synchronize()
+        rep_o = model.profile_report()
+        model.profile(False)
+        agree = float((model.segment(u8_dev, mean, std) == ref_mask).float().mean().item())
+        model.set_mode(args.mode)
+        top_o = max(rep_o, key=lambda k: rep_o[k][0]) if rep_o else None
+        other = {"mode": om, "value": world * B * args.steps / (ms_o * 1e-3), "unit": "crops/s", "ms_per_step": ms_o / args.steps,
+                 "mask_agreement_with_%s" % args.mode: agree,
+                 "kernels": {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps} for k, v in rep_o.items()},
+                 "top_kernel": top_o}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     hbm_peak, peak_src = peaks()
+    if other is not None:
+        for kname in ("esp_branch_tc_l3", "esp_branch_tc_l2", "esp_branch_l3", "esp_branch_l2"):
+            if kname in other["kernels"]:
+                kk = other["kernels"][kname]
+                other.setdefault("rooflines", {})[kname] = kernel_roofline(kname, kk["ms_per_step"] / kk["launches_per_step"], B, hbm_peak, peak_src)
     tot_ms = sum(v[0] for v in rep.values()) or 1.0
     kernels = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps, "share": v[0] / tot_ms} for k, v in rep.items()}
     top = max(rep, key=lambda k: rep[k][0]) if rep else None
@@ -301,23 +353,15 @@ def run_ours(args):
         per_launch_ms = rep[top][0] / rep[top][1]
         # algorithmic bytes of one esp_branch launch at level 3: per crop it reads o1 (25 ch) and the
         # residual (128 ch) and writes 128 ch of a 64x64 map, fp32
-        alg = {"esp_branch_l3": B * (25 + 128 + 128) * 64 * 64 * 4, "esp_branch_l2": B * (12 + 64 + 64) * 128 * 128 * 4}.get(top)
-        flops = {"esp_branch_l3": B * 4096 * 2 * 9 * 25 * 128, "esp_branch_l2": B * 16384 * 2 * 9 * 12 * 64}.get(top)
-        if alg is not None:
-            ach = alg / (per_launch_ms * 1e-3) / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_ms,
-                    "note": "fp32 mode: this kernel is CUDA-core FMA bound, not HBM bound (SURVEY.md 8(d)); see fp32_fma",
-                    "fp32_fma": {"achieved_tflops": flops / (per_launch_ms * 1e-3) / 1e12, "peak_tflops": FP32_FMA_PEAK_TFLOPS,
-                                 "frac": flops / (per_launch_ms * 1e-3) / 1e12 / FP32_FMA_PEAK_TFLOPS}}
+        roof = kernel_roofline(top, per_launch_ms, B, hbm_peak, peak_src)
 
-    cpu_sample = 4 if wl != "espnet_b256_ens5" else 1
-    cpu_val, cpu_dt = time_cpu(wl, cpu_sample, 3, 1) if world == 1 and not args.no_cpu else (None, None)
+    cpu_sample = 32 if wl != "espnet_b256_ens5" else 4
+    cpu_val, cpu_dt = time_cpu(wl, cpu_sample, 4, 1) if world == 1 and not args.no_cpu else (None, None)
     line = {
         "metric": "ESPNet 512x512 crops/s", "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl, B),
+        "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "f16 operands, f32 accumulate/storage", "data": "synthetic",
+        "config": dict(workload_config(wl, B), mode=args.mode),
         "mpx_per_s": value * H * W / 1e6,
         "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(u8_host.numel()), "d2h_bytes_per_step": int(mask_host.numel()),
                 "ms_per_step": ms_e2e / args.steps, "api": "model.segment(u8 crops) -> u8 class map, pinned host buffers"},
@@ -327,6 +371,8 @@ def run_ours(args):
         "clocks": clocks,
         "tflops_effective": value * (FLOP_PER_CROP_ENC if wl == "espnet_c_b64_fp32" else FLOP_PER_CROP_FULL) / 1e12,
     }
+    if other is not None:
+        line["other_mode"] = other
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": "crops/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "%d of the same synthetic 512x512 crops x 3 timed passes (%.1f s each), oracle port on torch %s CPU"
@@ -344,7 +390,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="espnet_c_b64_fp32", choices=["espnet_c_b64_fp32", "espnet_b64_fp32", "espnet_b256_ens5"])
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "f16tc"],
+                    help="fp32: CUDA-core FMA path (1e-3 logit bar); f16tc: tcgen05 fp16-operand path (0.999 mask-agreement bar)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--single-mode", action="store_true", help="skip the second leg that times the other compute mode")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -392,15 +392,17 @@ int run_branch(espnet_t* h, const BlockW& bw, const float* o1, const float* res,
 
 
 // ---------------------------------------------------------------------------------------------- tcgen05 path
-// fp16 tensor map over o1h [B][NKC][H][W][8] with a {8, 48, 48, NKC, 1} box, zero OOB fill, no swizzle
-int make_o1h_map(espnet_t* h, CUtensorMap* map, const __half* o1h, int B, int NKC, int H, int W) {
+// tensor map over the fp16 chunk-plane map o1h [B][NKC][H][W][8]: [W][8 halves] is presented as W*4 32-bit words so that
+// a box row is one contiguous 768 B run (a 16 B innermost box dimension makes TMA crawl); box {48*4, 48, NKC, 1},
+// zero OOB fill (= the conv zero padding), no swizzle
+int make_o1h_map(espnet_t* h, CUtensorMap* map, const __half* o1h, int B, int NKC, int H, int W, int box_w, int box_h, int box_planes) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NKC, (cuuint64_t)B};
-    cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)NKC * H * W * 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)kTcBox, (cuuint32_t)kTcBox, (cuuint32_t)NKC, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)o1h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)NKC, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)NKC * H * W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)box_w * 4, (cuuint32_t)box_h, (cuuint32_t)box_planes, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)o1h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled (o1h) failed with CUresult " + std::to_string((int)r));
     return ESPNET_OK;
@@ -446,15 +448,21 @@ int run_branch_tc(espnet_t* h, const BlockW& bw, const __half* o1h, const float*
     p.s2 = h->dparams + s2; p.t2 = h->dparams + t2; p.a2 = h->dparams + a2;
     p.out2 = out2; p.C2 = C2; p.c2_off = c2_off;
     p.B = B; p.H = H; p.W = W;
-    int rc = set_smem(h, esp_branch_tc_kernel<NKC, NOUT, CO1, CO>, Cfg::SMEM);
+    const int var = res == nullptr ? 0 : (out != nullptr ? 1 : 2);
+    if ((var == 0 && (!out || !out2)) || (var == 2 && !out2)) return fail(h, ESPNET_EINVAL, "run_branch_tc: unsupported output combination");
+    auto k0 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 0>;
+    auto k1 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 1>;
+    auto k2 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 2>;
+    auto kern = var == 0 ? k0 : (var == 1 ? k1 : k2);
+    int rc = set_smem(h, kern, Cfg::SMEM);
     if (rc) return rc;
     CUtensorMap map;
-    rc = make_o1h_map(h, &map, o1h, B, NKC, H, W);
+    rc = make_o1h_map(h, &map, o1h, B, NKC, H, W, kTcBoxW, kTcBoxH, 2);
     if (rc) return rc;
-    const long long tiles = (long long)B * ((H + kTcTile - 1) / kTcTile) * ((W + kTcTile - 1) / kTcTile);
+    const long long tiles = (long long)B * ((H + kTcTileH - 1) / kTcTileH) * ((W + kTcTileW - 1) / kTcTileW);
     const int grid = grid_for(h, tiles);
     { ProfScope _ps(h, NKC == 2 ? "esp_branch_tc_l2" : "esp_branch_tc_l3", st);
-      esp_branch_tc_kernel<NKC, NOUT, CO1, CO><<<grid, kTcThreads, Cfg::SMEM, st>>>(map, p); }
+      kern<<<grid, kTcThreads, Cfg::SMEM, st>>>(map, p); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -694,6 +702,8 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     const Workspace L = layout(h, a->B, a->H, a->W);
     if (a->workspace_bytes < L.total * sizeof(float)) return fail(h, ESPNET_ESTATE, "espnet_forward: workspace too small");
     if ((size_t)a->H * a->W > ((size_t)1 << 30)) return fail(h, ESPNET_ESHAPE, "espnet_forward: crop too large for 32-bit plane offsets");
+    if (h->mode == ESPNET_MODE_F16TC && (size_t)a->H * a->W > ((size_t)1 << 27))
+        return fail(h, ESPNET_ESHAPE, "espnet_forward: crop too large for the tensor-core path's 32-bit channel offsets");
 
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)a->stream;
@@ -838,7 +848,7 @@ int espnet_tc_selftest(int device, int nkc, int nout, int dy, int dx, int use_tm
     ST_TRY(cudaMemcpy(d_bw, bw.data(), bw.size() * 2, cudaMemcpyHostToDevice));
     ST_TRY(cudaMemset(d_out, 0xFF, (size_t)128 * nout * 4));
     CUtensorMap map;
-    int rc = make_o1h_map(nullptr, &map, d_map, 1, nkc, Hm, Wm);
+    int rc = make_o1h_map(nullptr, &map, d_map, 1, nkc, Hm, Wm, kTcBox, kTcBox, nkc);
     if (rc) { cleanup(); return rc; }
     const size_t smem = (size_t)4 * kTcPlaneBytes + 4 * 32 * 16 + 64;
     if (nout == 32) {

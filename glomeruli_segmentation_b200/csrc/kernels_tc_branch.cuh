@@ -1,0 +1,257 @@
+// tcgen05 / TMEM kernel of the ESP "split-transform-merge" stage (sm_100a): fp16 operands, fp32 accumulation in
+// tensor memory, fp32 epilogue.  ESPNET_MODE_F16TC of include/espnet_b200.h.
+//
+// Reference semantics: DilatedParllelResidualBlockB.forward (Model.py:187-214) and DownSamplerB.forward
+// (Model.py:144-160) after the c1 reduce: d_k = Conv3x3(dilation k, pad k)(o1) for k = 1,2,4,8,16, HFF prefix sums,
+// concat, residual add before BN, BN(eval, eps 1e-3) folded to scale/shift, PReLU.
+//
+// Work item = one M = 128 MMA tile = 8 columns x 16 rows of output pixels (TMEM lane l <-> row l/8, column l%8).
+//   * A operand: the reduced map o1 in fp16 "chunk-plane" layout [B][kc][H][W][8 ch] (tc_common.cuh).  TMA brings the
+//     tile plus the 16-pixel halo of the d = 16 branch (48 rows x 40 columns) into shared memory, two K chunks
+//     (= one K = 16 MMA step) per pipeline stage, two stages.  The tensor map presents [W][8 ch] as ONE dimension of
+//     32-bit words so that box rows are 640 B contiguous runs.  The zero padding of every conv is TMA's out-of-bounds
+//     fill.  Tap (ky,kx) of dilation d is the SAME buffer read through a UMMA descriptor whose start address is moved
+//     by ((ky-1)*d*40 + (kx-1)*d) * 16 B: the implicit-GEMM window shift costs no data movement.
+//   * B operand: all five branches' weights [br][tap][kc][NOUT][8] fp16, resident in shared memory for the whole
+//     persistent CTA (one cp.async.bulk at kernel start; 90 KB at level 3, 22.5 KB at level 2).
+//   * D: five accumulators of NOUT fp32 columns per tile, THREE tiles deep in TMEM, so that the epilogue of tile i
+//     runs while TMA and the tensor core work on tiles i+1 and i+2.
+//   * MMA order per tile: K step outer, (branch, tap) inner -- stage s only needs the K chunks of step s, so the TMA
+//     of the next tile's first half overlaps the second half's MMAs.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//     warps 4..11 = epilogue: TMEM -> registers, HFF sums, residual + BN + PReLU, planar fp32 stores; warp e works on
+//     TMEM lanes 32*(e%4).. and on the accumulator column groups g = e/4 (mod 2).
+#pragma once
+#include "kernels_fp32.cuh"
+#include "tc_common.cuh"
+
+namespace espnet {
+
+constexpr int kTcTileW = 8;                          // output tile: 8 columns x 16 rows = 128 pixels = MMA M
+constexpr int kTcTileH = 16;
+constexpr int kTcHalo2 = 16;                         // largest dilation
+constexpr int kTcBoxW = kTcTileW + 2 * kTcHalo2;     // 40
+constexpr int kTcBoxH = kTcTileH + 2 * kTcHalo2;     // 48
+constexpr int kTcPlane2 = kTcBoxH * kTcBoxW * 16;    // bytes of one K chunk plane of the box: 30720
+constexpr int kTcStage = 2 * kTcPlane2;              // one pipeline stage = 2 K chunks = one K = 16 MMA step: 61440
+constexpr int kTcThreads = 384;
+constexpr int kTcAccStages = 3;
+
+struct BranchTcParams {
+    const __half* w;        // [5][9][NKC][NOUT][8] fp16 (d1, d2, d4, d8, d16)
+    const float* res;       // [B,C,H,W] residual input or nullptr
+    const float *s, *t, *a; // BN scale/shift + PReLU slope (C)
+    float* out;             // [B,C,H,W] or nullptr
+    const float *s2, *t2, *a2;
+    float* out2;            // [B,C2,H,W] or nullptr (second BR straight into the following concat buffer)
+    int C2, c2_off;
+    int B, H, W;
+};
+
+template <int NKC, int NOUT>
+struct BranchTcCfg {
+    static constexpr int KS = NKC / 2;                            // K = 16 steps per tile
+    static constexpr int W_BRANCH = 9 * NKC * NOUT * 16;          // bytes of one branch's weights
+    static constexpr int W_BYTES = 5 * W_BRANCH;
+    static constexpr int ACC_COLS = 5 * NOUT;                     // TMEM columns per tile
+    static constexpr int TMEM_COLS = (kTcAccStages * ACC_COLS <= 256) ? 256 : 512;
+    static constexpr int EP_BYTES = 2 * 128 * 16;                 // two float4 tables of 128 channels
+    static constexpr size_t SMEM = 1024 + 2 * (size_t)kTcStage + (size_t)W_BYTES + EP_BYTES + 256;
+    static_assert(kTcAccStages * ACC_COLS <= 512, "TMEM columns");
+};
+
+// VAR: 0 = DownSamplerB (no residual, writes out and out2), 1 = ESP block (residual, out), 2 = last ESP block of a level
+// (residual, writes only the BR'd copy into the following concat buffer)
+template <int NKC, int NOUT, int CO1, int CO, int VAR>
+__global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BranchTcParams p) {
+    using Cfg = BranchTcCfg<NKC, NOUT>;
+    constexpr int C = CO1 + 4 * CO;
+    constexpr int KS = Cfg::KS;
+    static_assert(C <= 128 && CO1 <= NOUT && CO <= NOUT && (NOUT == 16 || NOUT == 32), "channel counts");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [A stage 0 | A stage 1 | weights | epilogue params | barriers | tmem slot]
+    uint8_t* abuf = smem_raw;
+    uint8_t* wbuf = abuf + 2 * kTcStage;
+    float4* sep4 = reinterpret_cast<float4*>(wbuf + Cfg::W_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sep4) + Cfg::EP_BYTES);
+    uint64_t* a_full = bars + 0;      // [2]
+    uint64_t* a_empty = bars + 2;     // [2]
+    uint64_t* w_full = bars + 4;
+    uint64_t* acc_full = bars + 5;    // [3]
+    uint64_t* acc_empty = bars + 8;   // [3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = p.H, W = p.W;
+    const int tiles_x = (W + kTcTileW - 1) / kTcTileW, tiles_y = (H + kTcTileH - 1) / kTcTileH;
+    const int total_tiles = p.B * tiles_x * tiles_y;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (tid == 0) {
+        if ((tc::smem_addr(abuf) & 127u) != 0) __trap();   // TMA destination alignment
+        tc::mbar_init(a_full + 0, 1); tc::mbar_init(a_full + 1, 1);
+        tc::mbar_init(a_empty + 0, 1); tc::mbar_init(a_empty + 1, 1);
+        tc::mbar_init(w_full, 1);
+        for (int s = 0; s < kTcAccStages; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 8); }
+        tc::mbar_fence_init();
+        tc::tma_prefetch_desc(&tmap);
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    // epilogue params as float4 (scale, shift, slope, -): [0,128) own BN + PReLU, [128,256) the second BR
+    for (int i = tid; i < C; i += kTcThreads) {
+        sep4[i] = make_float4(p.s[i], p.t[i], p.a[i], 0.f);
+        if (VAR != 1) sep4[128 + i] = make_float4(p.s2[p.c2_off + i], p.t2[p.c2_off + i], p.a2[p.c2_off + i], 0.f);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: weights once, then one half-box (2 K chunks) per pipeline step =====
+        if (lane == 0) {
+            tc::mbar_expect_tx(w_full, Cfg::W_BYTES);
+            tc::bulk_g2s(wbuf, p.w, Cfg::W_BYTES, w_full);
+            int c = 0;   // chunk counter: chunk c of this CTA = (tile c / KS, K step c % KS), stage c & 1
+            for (int it = 0; it < my_tiles; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks, ++c) {
+                    const int s = c & 1;
+                    tc::mbar_wait(a_empty + s, (uint32_t)(((c >> 1) & 1) ^ 1));
+                    tc::mbar_expect_tx(a_full + s, kTcStage);
+                    tc::tma_load_4d(abuf + s * kTcStage, &tmap, a_full + s, 4 * (tx * kTcTileW - kTcHalo2), ty * kTcTileH - kTcHalo2, 2 * ks, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
+            // Descriptors as (hi, lo) words: hi = SBO | version is constant per operand, lo = start>>4 | LBO<<12 and
+            // every window shift / tap is an ADD on lo in 16 B units.  One thread issues everything, so the per-MMA
+            // instruction count IS the issue rate: taps are unrolled with constant offsets.
+            constexpr uint32_t a_hi = (uint32_t)((kTcBoxW * 16) >> 4) | (1u << 14);
+            constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+            const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + (uint32_t)(kTcHalo2 * kTcBoxW + kTcHalo2) + ((uint32_t)(kTcPlane2 >> 4) << 16);
+            const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
+            tc::mbar_wait(w_full, 0);
+            int c = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int as = it % kTcAccStages;
+                tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
+                const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks, ++c) {
+                    const int s = c & 1;
+                    tc::mbar_wait(a_full + s, (uint32_t)((c >> 1) & 1));
+                    tc::tc_fence_after();
+                    const uint32_t a_lo_s = a_lo0 + (uint32_t)(s * (kTcStage >> 4));
+                    const uint32_t b_lo_s = b_lo0 + (uint32_t)(2 * ks * NOUT);
+#pragma unroll 1
+                    for (int br = 0; br < 5; ++br) {
+                        const int d = 1 << br, dp = d * kTcBoxW;
+                        const uint32_t b_lo = b_lo_s + (uint32_t)(br * (Cfg::W_BRANCH >> 4));
+                        const uint32_t d_tmem = d_tile + (uint32_t)(br * NOUT);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3 - 1, kx = tap % 3 - 1;           // compile-time after unrolling
+                            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + (uint32_t)(ky * dp + kx * d));
+                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(tap * (NKC * NOUT)));
+                            tc::umma_f16(d_tmem, adesc, bdesc, idesc, (ks | tap) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc::umma_commit(a_empty + s);           // this half-box is reusable once the MMAs above have read it
+                }
+                tc::umma_commit(acc_full + as);             // accumulators of this tile complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps; thread <-> pixel (TMEM lane), so a warp touches 4 rows x 32 B per channel plane =====
+        constexpr bool HAS_RES = VAR != 0, HAS_OUT = VAR != 2, HAS_OUT2 = VAR != 1;
+        constexpr int NG = NOUT / 8;                                   // groups of 8 accumulator columns
+        const int e = warp - 4, q = e & 3, gpar = e >> 2;
+        const int row = 4 * q + (lane >> 3), col = lane & 7;
+        const size_t plane = (size_t)H * W;
+        const uint32_t plane_b = (uint32_t)(plane * sizeof(float));   // host guarantees C * plane * 4 < 2^32
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+            const int y = ty * kTcTileH + row, x = tx * kTcTileW + col;
+            const bool valid = (y < H) && (x < W);
+            const size_t pix = valid ? (size_t)y * W + x : 0;
+            // byte pointers to channel 0 of this pixel; a channel is "+ ch * plane_b" = one IMAD.WIDE.U32
+            const char* res_b = HAS_RES ? reinterpret_cast<const char*>(p.res + (size_t)b * C * plane + pix) : nullptr;
+            char* out_b = HAS_OUT ? reinterpret_cast<char*>(p.out + (size_t)b * C * plane + pix) : nullptr;
+            char* out2_b = HAS_OUT2 ? reinterpret_cast<char*>(p.out2 + ((size_t)b * p.C2 + p.c2_off) * plane + pix) : nullptr;
+            const int as = it % kTcAccStages;
+            const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * Cfg::ACC_COLS);
+            bool waited = false;
+
+            // Column group g = accumulator columns [8g, 8g+8) of all five branches.  The 40 residual loads of the group
+            // are issued BEFORE the accumulators are waited for (memory-level parallelism: the epilogue is the HBM
+            // side of this kernel), then 5 TMEM loads, the HFF prefix sums add1..add4 (Model.py:152-155,203-206) in 8
+            // registers, and per concat channel: residual add BEFORE BN (Model.py:211-212), folded BN + PReLU, optional
+            // second BR.  The g loop stays rolled: small code, nothing hoisted into spills.
+#pragma unroll 1
+            for (int g = gpar; g < NG; g += 2) {
+                const uint32_t goff = (uint32_t)(8 * g) * plane_b;
+                float rv[5][8];
+#pragma unroll
+                for (int br = 0; br < 5; ++br) {
+                    const int ch0 = br == 0 ? 0 : CO1 + (br - 1) * CO;
+                    const int cnt = br == 0 ? CO1 : CO;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        rv[br][jj] = 0.f;
+                        if (HAS_RES && valid && 8 * g + jj < cnt)
+                            rv[br][jj] = __ldg(reinterpret_cast<const float*>(res_b + goff + (uint64_t)plane_b * (uint32_t)(ch0 + jj)));
+                    }
+                }
+                if (!waited) {
+                    tc::mbar_wait(acc_full + as, (uint32_t)((it / kTcAccStages) & 1));
+                    tc::tc_fence_after();
+                    waited = true;
+                }
+                uint32_t r[5][8];
+                __syncwarp();    // tcgen05.ld is .sync.aligned: the lanes diverged on `valid` in the previous group
+#pragma unroll
+                for (int br = 0; br < 5; ++br) tc::tmem_ld8_nowait(t0 + (uint32_t)(br * NOUT + 8 * g), r[br]);
+                tc::tmem_ld_wait();
+                if (!valid) continue;
+                float run[8];
+#pragma unroll
+                for (int br = 0; br < 5; ++br) {
+                    const int ch0 = br == 0 ? 0 : CO1 + (br - 1) * CO;     // first concat channel of this slice
+                    const int cnt = br == 0 ? CO1 : CO;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const float d = __uint_as_float(r[br][jj]);
+                        run[jj] = br <= 1 ? d : run[jj] + d;
+                        if (8 * g + jj >= cnt) continue;
+                        const float4 q1 = sep4[ch0 + 8 * g + jj];
+                        const float o = bn_prelu(run[jj] + rv[br][jj], q1.x, q1.y, q1.z);
+                        if (HAS_OUT) *reinterpret_cast<float*>(out_b + goff + (uint64_t)plane_b * (uint32_t)(ch0 + jj)) = o;
+                        if (HAS_OUT2) {
+                            const float4 q2 = sep4[128 + ch0 + 8 * g + jj];
+                            *reinterpret_cast<float*>(out2_b + goff + (uint64_t)plane_b * (uint32_t)(ch0 + jj)) = bn_prelu(o, q2.x, q2.y, q2.z);
+                        }
+                    }
+                }
+            }
+            if (!waited) {   // (cannot happen for NOUT >= 16, kept for safety: every warp must consume the phase)
+                tc::mbar_wait(acc_full + as, (uint32_t)((it / kTcAccStages) & 1));
+                tc::tc_fence_after();
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + as);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace espnet
