@@ -17,6 +17,7 @@
 #include "kernels_fp32.cuh"
 #include "kernels_fp32_tma.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc_reduce.cuh"
 #include "kernels_wsi.cuh"
 
 using namespace espnet;
@@ -41,7 +42,8 @@ struct HostTensor {
 // offsets (in floats) of the packed, kernel-ready parameter arrays inside the device blob
 struct BlockW {
     size_t c1 = 0, d1 = 0, chain = 0, s = 0, t = 0, a = 0;
-    size_t tc = 0;   // offset (bytes) into the fp16 blob for the tensor-core path
+    size_t tc = 0;   // offset (bytes) into the fp16 blob for the tensor-core path: branch weights
+    size_t tc_c1 = 0;   // ... and the 1x1 reduce weights [CIN/8][NOUT][8] (ESP blocks only)
 };
 
 struct Packed {
@@ -81,6 +83,7 @@ struct espnet_handle {
     size_t nparams_h = 0;
     Packed pk;
     std::map<std::string, StageRef> stages;
+    int tc_reduce = 1;     // f16tc mode: 1 = 1x1 reduce on tensor cores, 0 = CUDA-core fp32 reduce rounded to fp16 ("tc_reduce")
     int branch_impl = 0;   // 0 auto, 1 per-thread global loads, 2 TMA-staged (espnet_set_option "branch_impl")
     // per-kernel CUDA-event timing (espnet_set_profiling)
     bool profiling = false;
@@ -240,6 +243,22 @@ struct Packer {
                             dst[((((size_t)b * 9 + t) * nkc + c / 8) * nout + o) * 8 + (c % 8)] = bits;
                         }
             }
+        }
+        if (!down) {   // tensor-core 1x1 reduce: [CIN/8][NOUT][8] fp16, element (kc, o, j) = W1[o][8 kc + j]
+            const int nout = 8 * (2 * ((n + 15) / 16));     // = 8 * NKC of the branch kernel's A operand
+            const HostTensor* w = get(key + ".c1.conv.weight", {n, cin, 1, 1});
+            if (!w) return false;
+            while (blob_h.size() % 64) blob_h.push_back(0);
+            bw.tc_c1 = blob_h.size() * sizeof(uint16_t);
+            blob_h.resize(blob_h.size() + (size_t)(cin / 8) * nout * 8, 0);
+            uint16_t* dst = blob_h.data() + bw.tc_c1 / sizeof(uint16_t);
+            for (int o = 0; o < n; ++o)
+                for (int c = 0; c < cin; ++c) {
+                    const __half hv = __float2half_rn(w->data[(size_t)o * cin + c]);
+                    uint16_t bits;
+                    std::memcpy(&bits, &hv, 2);
+                    dst[((size_t)(c / 8) * nout + o) * 8 + (c % 8)] = bits;
+                }
         }
         const std::string bnk = down ? key + ".bn" : key + ".bn.bn";
         const std::string ak = down ? key + ".act.weight" : key + ".bn.act.weight";
@@ -418,6 +437,20 @@ int run_reduce1x1_f16(espnet_t* h, const float* in, size_t w_off, __half* o1h, i
     if (ctas > cap) ctas = cap;
     { ProfScope _ps(h, CIN == 64 ? "reduce1x1_f16_l2" : "reduce1x1_f16_l3", st);
       reduce1x1_f16_kernel<CIN, CO, NKC><<<(int)ctas, 256, smem, st>>>(in, h->dparams + w_off, o1h, B, HW); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+template <int CIN, int NOUT, int NKC>
+int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h, int B, int H, int W, cudaStream_t st) {
+    using Cfg = ReduceTcCfg<CIN, NOUT>;
+    const int HW = H * W;
+    int rc = set_smem(h, reduce1x1_tc_kernel<CIN, NOUT, NKC>, Cfg::SMEM);
+    if (rc) return rc;
+    const int grid = grid_for(h, (long long)B * ((HW + 127) / 128));
+    { ProfScope _ps(h, CIN == 64 ? "reduce1x1_tc_l2" : "reduce1x1_tc_l3", st);
+      reduce1x1_tc_kernel<CIN, NOUT, NKC><<<grid, kRedThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + bw.tc_c1), o1h, B, HW); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -614,6 +647,7 @@ int espnet_set_mode(espnet_t* h, int mode) {
 int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (!h || !key) return ESPNET_EINVAL;
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 1) { h->tc_reduce = value; return ESPNET_OK; }
     return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);
 }
 
@@ -749,7 +783,8 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     auto block_l2 = [&](const BlockW& bw, bool down, const float* in, float* out, float* out2, int c2_off) -> int {
         int r;
         if (tcm) {
-            r = down ? run_reduce3x3_f16<19, 12, 2>(h, in, bw.c1, o1h, B, H2, W2, st) : run_reduce1x1_f16<64, 12, 2>(h, in, bw.c1, o1h, B, H4, W4, st);
+            r = down ? run_reduce3x3_f16<19, 12, 2>(h, in, bw.c1, o1h, B, H2, W2, st)
+                     : (h->tc_reduce ? run_reduce1x1_tc<64, 16, 2>(h, in, bw, o1h, B, H4, W4, st) : run_reduce1x1_f16<64, 12, 2>(h, in, bw.c1, o1h, B, H4, W4, st));
             if (r) return r;
             return run_branch_tc<2, 16, 16, 12>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
         }
@@ -760,7 +795,8 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     auto block_l3 = [&](const BlockW& bw, bool down, const float* in, float* out, float* out2, int c2_off) -> int {
         int r;
         if (tcm) {
-            r = down ? run_reduce3x3_f16<131, 25, 4>(h, in, bw.c1, o1h, B, H4, W4, st) : run_reduce1x1_f16<128, 25, 4>(h, in, bw.c1, o1h, B, H8, W8, st);
+            r = down ? run_reduce3x3_f16<131, 25, 4>(h, in, bw.c1, o1h, B, H4, W4, st)
+                     : (h->tc_reduce ? run_reduce1x1_tc<128, 32, 4>(h, in, bw, o1h, B, H8, W8, st) : run_reduce1x1_f16<128, 25, 4>(h, in, bw.c1, o1h, B, H8, W8, st));
             if (r) return r;
             return run_branch_tc<4, 32, 28, 25>(h, bw, o1h, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
         }

@@ -22,6 +22,9 @@ constexpr int kRows = 4;  // pixels (rows) per thread in the register tile
 #ifndef ESPNET_PIPE
 #define ESPNET_PIPE 0
 #endif
+#ifndef ESPNET_TAPROLL
+#define ESPNET_TAPROLL 0
+#endif
 #ifndef ESPNET_G25
 #define ESPNET_G25 5
 #endif

@@ -63,6 +63,50 @@ template <int N, int CO>
 __device__ __forceinline__ void tma_stage_compute(float (&acc)[kRows][CO], const float* __restrict__ box, int nc, int c0, int d,
                                                   int ly, int lx, int gy0, int H, const float* __restrict__ wsm) {
     constexpr int CP = pad4(CO);
+#if ESPNET_TAPROLL == 1
+    // rolled tap rows: the hot body is 3 (tap, channel) steps = ~370 instructions (~6 KB), it stays in the instruction
+    // cache (the fully unrolled 9-tap body is ~18 KB per instantiation and ncu showed stall_no_instruction on top)
+#pragma unroll 1
+    for (int cc = 0; cc < nc; ++cc) {
+        const float* bc = box + cc * (kTmaBox * kTmaBox) + (ly + kTmaHalo) * kTmaBox + lx + kTmaHalo;
+        const float* wc = wsm + (size_t)(c0 + cc) * CP;
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ++ky) {
+            const int dy = (ky - 1) * d;
+            if (gy0 + kRows - 1 + dy < 0 || gy0 + dy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* s = bc + dy * kTmaBox + (kx - 1) * d;
+                float a[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) a[r] = s[r * kTmaBox];
+                fma_tile<CO>(acc, a, wc + (size_t)(ky * 3 + kx) * N * CP);
+            }
+        }
+    }
+    return;
+#elif ESPNET_TAPROLL == 2
+    // rolled tap rows, both channels of the stage inside the body: 6 steps = ~740 instructions (~12 KB)
+#pragma unroll 1
+    for (int ky = 0; ky < 3; ++ky) {
+        const int dy = (ky - 1) * d;
+        if (gy0 + kRows - 1 + dy < 0 || gy0 + dy >= H) continue;
+#pragma unroll 2
+        for (int cc = 0; cc < nc; ++cc) {
+            const float* bc = box + cc * (kTmaBox * kTmaBox) + (ly + kTmaHalo) * kTmaBox + lx + kTmaHalo;
+            const float* wc = wsm + (size_t)(c0 + cc) * CP;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* s = bc + dy * kTmaBox + (kx - 1) * d;
+                float a[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) a[r] = s[r * kTmaBox];
+                fma_tile<CO>(acc, a, wc + (size_t)(ky * 3 + kx) * N * CP);
+            }
+        }
+    }
+    return;
+#endif
 #pragma unroll 1
     for (int cc = 0; cc < nc; ++cc) {
         const float* bc = box + cc * (kTmaBox * kTmaBox) + (ly + kTmaHalo) * kTmaBox + lx + kTmaHalo;

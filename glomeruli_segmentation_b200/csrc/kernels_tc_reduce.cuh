@@ -1,0 +1,155 @@
+// tcgen05 kernel of the ESP block's 1x1 reduce (Model.py:178,192: c1 = C(nIn, n, 1, 1)), ESPNET_MODE_F16TC.
+//
+// o1[px][co] = sum_ci x[px][ci] * W1[co][ci] as a plain GEMM: M = 128 consecutive pixels of one crop, N = NOUT
+// (12 -> 16, 25 -> 32 output channels), K = CIN (64 / 128).  The input is the previous block's planar fp32 output; the
+// loader warps read it coalesced (lanes = consecutive pixels of one channel plane), round once to fp16 and store it as
+// the K-major chunk-plane A operand [kc][128 px][8 ch] (tc_common.cuh) -- the transpose is free because a thread owns a
+// pixel and writes one 16 B chunk per 8 channels.  The result leaves TMEM as fp16 chunk-plane o1h [B][kc][HW][8], the
+// layout the branch kernel's TMA box reads.  HBM-bound: 4*CIN + 2*8*NKC bytes per pixel.
+//   warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = loaders (pixel quarter x channel half),
+//   warps 12..15 = epilogue; A is double-buffered, accumulators are two tiles deep.
+#pragma once
+#include "kernels_fp32.cuh"
+#include "tc_common.cuh"
+
+namespace espnet {
+
+constexpr int kRedThreads = 512;
+
+template <int CIN, int NOUT>
+struct ReduceTcCfg {
+    static constexpr int KC = CIN / 8;                 // input K chunks
+    static constexpr int A_STAGE = KC * 128 * 16;      // bytes
+    static constexpr int W_BYTES = KC * NOUT * 16;
+    static constexpr size_t SMEM = 1024 + 2 * (size_t)A_STAGE + W_BYTES + 256;
+};
+
+// w: [CIN/8][NOUT][8] fp16, element (kc, n, j) = W1[co = n][ci = 8 kc + j] (zero for n >= CO)
+template <int CIN, int NOUT, int NKC>
+__global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const float* __restrict__ in, const __half* __restrict__ w,
+                                                                      __half* __restrict__ o1h, int B, int HW) {
+    using Cfg = ReduceTcCfg<CIN, NOUT>;
+    constexpr int KC = Cfg::KC;
+    static_assert(CIN % 16 == 0 && NKC * 8 == NOUT, "shapes");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* abuf = smem_raw;
+    uint8_t* wbuf = abuf + 2 * Cfg::A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + Cfg::W_BYTES);
+    uint64_t* a_full = bars + 0;      // [2] 8 loader warps arrive
+    uint64_t* a_empty = bars + 2;     // [2] MMA commit
+    uint64_t* acc_full = bars + 4;    // [2]
+    uint64_t* acc_empty = bars + 6;   // [2] 4 epilogue warps arrive
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunks = (HW + 127) / 128;
+    const int total_tiles = B * chunks;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(a_full + s, 8); tc::mbar_init(a_empty + s, 1);
+            tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 4);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, 64);
+    for (int i = tid; i < Cfg::W_BYTES / 16; i += kRedThreads) reinterpret_cast<uint4*>(wbuf)[i] = __ldg(reinterpret_cast<const uint4*>(w) + i);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
+            constexpr uint32_t a_hi = (uint32_t)(128 >> 4) | (1u << 14);
+            constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+            const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + ((uint32_t)(2048 >> 4) << 16);
+            const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it & 1;
+                tc::mbar_wait(acc_empty + s, (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc::mbar_wait(a_full + s, (uint32_t)((it >> 1) & 1));
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * 32);
+#pragma unroll
+                for (int ks = 0; ks < KC / 2; ++ks) {
+                    const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(s * (Cfg::A_STAGE >> 4) + 2 * ks * (2048 >> 4)));
+                    const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(2 * ks * NOUT));
+                    tc::umma_f16(d_tmem, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+                }
+                tc::umma_commit(a_empty + s);
+                tc::umma_commit(acc_full + s);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== loaders: warp lw -> pixels 32*(lw%4) + lane, K chunks [(lw/4) * KC/2, +KC/2) =====
+        const int lw = warp - 4, px = 32 * (lw & 3) + lane, kc0 = (lw >> 2) * (KC / 2);
+        const uint32_t plane_b = (uint32_t)HW * 4u;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int b = tile / chunks, p = (tile % chunks) * 128 + px;
+            const bool ok = p < HW;
+            const char* src = reinterpret_cast<const char*>(in + (size_t)b * CIN * HW + (ok ? p : 0));
+            const int s = it & 1;
+            uint8_t* dst = abuf + s * Cfg::A_STAGE + px * 16;
+            // issue this tile's global loads before waiting for the smem slot: the slot wait is hidden behind them
+            float v[KC / 2][8];
+#pragma unroll
+            for (int k = 0; k < KC / 2; ++k)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[k][j] = ok ? __ldg(reinterpret_cast<const float*>(src + (uint64_t)plane_b * (uint32_t)(8 * (kc0 + k) + j))) : 0.f;
+            tc::mbar_wait(a_empty + s, (uint32_t)(((it >> 1) & 1) ^ 1));
+#pragma unroll
+            for (int k = 0; k < KC / 2; ++k) {
+                __half2 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[k][2 * j], v[k][2 * j + 1]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                *reinterpret_cast<uint4*>(dst + (kc0 + k) * 2048) = u;
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(a_full + s);
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue: TMEM -> fp16 chunk-plane o1h =====
+        const int q = warp & 3, px = 32 * q + lane;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int b = tile / chunks, p = (tile % chunks) * 128 + px;
+            const int s = it & 1;
+            tc::mbar_wait(acc_full + s, (uint32_t)((it >> 1) & 1));
+            tc::tc_fence_after();
+            float v[NOUT];
+            const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * 32);
+            if constexpr (NOUT == 32) tc::tmem_ld32(t0, v); else tc::tmem_ld16(t0, v);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + s);
+            if (p < HW) {
+#pragma unroll
+                for (int kc = 0; kc < NKC; ++kc) {
+                    __half2 h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[8 * kc + 2 * j], v[8 * kc + 2 * j + 1]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                    u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                    *reinterpret_cast<uint4*>(o1h + (((size_t)b * NKC + kc) * HW + p) * 8) = u;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 64);
+}
+
+}  // namespace espnet
