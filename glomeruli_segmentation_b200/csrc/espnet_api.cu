@@ -18,6 +18,7 @@
 #include "kernels_fp32_tma.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc_reduce.cuh"
+#include "kernels_tc_down.cuh"
 #include "kernels_wsi.cuh"
 
 using namespace espnet;
@@ -244,6 +245,23 @@ struct Packer {
                         }
             }
         }
+        if (down) {    // tensor-core 3x3 stride-2 reduce: [ks][tap][2 chunks][NOUT][8] fp16, element = W[o][16 ks + 8 kc + j][tap]
+            const int nout = 8 * (2 * ((n + 15) / 16)), ks_n = (cin + 15) / 16;
+            const HostTensor* w = get(key + ".c1.conv.weight", {n, cin, 3, 3});
+            if (!w) return false;
+            while (blob_h.size() % 64) blob_h.push_back(0);
+            bw.tc_c1 = blob_h.size() * sizeof(uint16_t);
+            blob_h.resize(blob_h.size() + (size_t)ks_n * 9 * 2 * nout * 8, 0);
+            uint16_t* dst = blob_h.data() + bw.tc_c1 / sizeof(uint16_t);
+            for (int o = 0; o < n; ++o)
+                for (int c = 0; c < cin; ++c)
+                    for (int t = 0; t < 9; ++t) {
+                        const __half hv = __float2half_rn(w->data[((size_t)o * cin + c) * 9 + t]);
+                        uint16_t bits;
+                        std::memcpy(&bits, &hv, 2);
+                        dst[(((((size_t)(c / 16) * 9 + t) * 2 + (c % 16) / 8) * nout + o) * 8) + (c % 8)] = bits;
+                    }
+        }
         if (!down) {   // tensor-core 1x1 reduce: [CIN/8][NOUT][8] fp16, element (kc, o, j) = W1[o][8 kc + j]
             const int nout = 8 * (2 * ((n + 15) / 16));     // = 8 * NKC of the branch kernel's A operand
             const HostTensor* w = get(key + ".c1.conv.weight", {n, cin, 1, 1});
@@ -451,6 +469,20 @@ int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
     const int grid = grid_for(h, (long long)B * ((HW + 127) / 128));
     { ProfScope _ps(h, CIN == 64 ? "reduce1x1_tc_l2" : "reduce1x1_tc_l3", st);
       reduce1x1_tc_kernel<CIN, NOUT, NKC><<<grid, kRedThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + bw.tc_c1), o1h, B, HW); }
+    LAUNCH_COUNT();
+    CUDA_TRY(h, cudaPeekAtLastError());
+    return ESPNET_OK;
+}
+
+template <int CIN, int NOUT, int NKC>
+int run_reduce3x3_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h, int B, int Hi, int Wi, cudaStream_t st) {
+    using Cfg = DownTcCfg<CIN, NOUT>;
+    int rc = set_smem(h, reduce3x3s2_tc_kernel<CIN, NOUT, NKC>, Cfg::SMEM);
+    if (rc) return rc;
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    const int grid = grid_for(h, (long long)B * ((Ho + 15) / 16) * ((Wo + 7) / 8));
+    { ProfScope _ps(h, CIN == 19 ? "reduce3x3s2_tc_l2" : "reduce3x3s2_tc_l3", st);
+      reduce3x3s2_tc_kernel<CIN, NOUT, NKC><<<grid, kDownThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + bw.tc_c1), o1h, B, Hi, Wi); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -783,7 +815,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     auto block_l2 = [&](const BlockW& bw, bool down, const float* in, float* out, float* out2, int c2_off) -> int {
         int r;
         if (tcm) {
-            r = down ? run_reduce3x3_f16<19, 12, 2>(h, in, bw.c1, o1h, B, H2, W2, st)
+            r = down ? (h->tc_reduce ? run_reduce3x3_tc<19, 16, 2>(h, in, bw, o1h, B, H2, W2, st) : run_reduce3x3_f16<19, 12, 2>(h, in, bw.c1, o1h, B, H2, W2, st))
                      : (h->tc_reduce ? run_reduce1x1_tc<64, 16, 2>(h, in, bw, o1h, B, H4, W4, st) : run_reduce1x1_f16<64, 12, 2>(h, in, bw.c1, o1h, B, H4, W4, st));
             if (r) return r;
             return run_branch_tc<2, 16, 16, 12>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
@@ -795,7 +827,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     auto block_l3 = [&](const BlockW& bw, bool down, const float* in, float* out, float* out2, int c2_off) -> int {
         int r;
         if (tcm) {
-            r = down ? run_reduce3x3_f16<131, 25, 4>(h, in, bw.c1, o1h, B, H4, W4, st)
+            r = down ? (h->tc_reduce ? run_reduce3x3_tc<131, 32, 4>(h, in, bw, o1h, B, H4, W4, st) : run_reduce3x3_f16<131, 25, 4>(h, in, bw.c1, o1h, B, H4, W4, st))
                      : (h->tc_reduce ? run_reduce1x1_tc<128, 32, 4>(h, in, bw, o1h, B, H8, W8, st) : run_reduce1x1_f16<128, 25, 4>(h, in, bw.c1, o1h, B, H8, W8, st));
             if (r) return r;
             return run_branch_tc<4, 32, 28, 25>(h, bw, o1h, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);

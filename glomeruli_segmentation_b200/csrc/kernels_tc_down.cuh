@@ -1,0 +1,206 @@
+// tcgen05 kernel of DownSamplerB's c1 (Model.py:135,145: C(nIn, n, 3, 2) = 3x3, stride 2, pad 1, no bias), F16TC mode.
+//
+// Implicit GEMM: M = 128 output pixels (8 columns x 16 rows, TMEM lane l <-> row l/8, column l%8), N = NOUT (12 -> 16,
+// 25 -> 32), K = 9 taps x CIN (19 -> 32, 131 -> 144 input channels, padded to K = 16 steps).
+// A stride-2 tap reads every second input column, so the loader warps split the staged input by COLUMN PARITY while they
+// convert it from planar fp32 to the fp16 K-major chunk-plane operand layout (tc_common.cuh):
+//     region = input rows 2*oy0-1 .. 2*oy0+31 (33) x columns 2*ox0-1 .. 2*ox0+15 (17), zero outside the map (= pad 1)
+//     smem   = [K chunk][parity][33 rows][9 entries][8 ch]        parity 1: columns 2*ox0-1, +1, ..   parity 0: 2*ox0, +2, ..
+// Output column x then finds tap kx at parity (kx != 1), entry (x - ox0) + (kx == 2): eight consecutive output pixels are
+// eight consecutive 16 B entries = one UMMA core matrix, the next output row is two input rows further (SBO = 2*9*16 B),
+// and tap ky is a start-address shift of ky rows.  One pipeline stage = one K = 16 step (16 input channels of the region,
+// 19 KB); the weights of all taps and K steps stay resident in shared memory (81 KB at level 3).
+//   warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = loaders, warps 12..15 = epilogue (fp16 chunk-plane o1h).
+#pragma once
+#include "kernels_fp32.cuh"
+#include "tc_common.cuh"
+
+namespace espnet {
+
+constexpr int kDownThreads = 512;
+constexpr int kDownRows = 33, kDownCols = 17, kDownPitch = 9;
+constexpr int kDownParBytes = kDownRows * kDownPitch * 16;      // one parity plane of one K chunk: 4752
+constexpr int kDownChunkBytes = 2 * kDownParBytes;              // 9504
+constexpr int kDownStageBytes = 2 * kDownChunkBytes;            // 19008: two K chunks = one K = 16 step
+constexpr int kDownStages = 4;
+
+template <int CIN, int NOUT>
+struct DownTcCfg {
+    static constexpr int KS = (CIN + 15) / 16;                  // K = 16 steps
+    static constexpr int W_BYTES = KS * 9 * 2 * NOUT * 16;      // [ks][tap][2 chunks][NOUT][8] fp16
+    static constexpr size_t SMEM = 1024 + (size_t)kDownStages * kDownStageBytes + W_BYTES + 256;
+};
+
+template <int CIN, int NOUT, int NKC>
+__global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const float* __restrict__ in, const __half* __restrict__ w,
+                                                                        __half* __restrict__ o1h, int B, int Hi, int Wi) {
+    using Cfg = DownTcCfg<CIN, NOUT>;
+    constexpr int KS = Cfg::KS;
+    static_assert(NKC * 8 == NOUT, "shapes");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* abuf = smem_raw;
+    uint8_t* wbuf = abuf + kDownStages * kDownStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + Cfg::W_BYTES);
+    uint64_t* a_full = bars + 0;                    // [4] 8 loader warps arrive
+    uint64_t* a_empty = bars + kDownStages;         // [4] MMA commit
+    uint64_t* acc_full = bars + 2 * kDownStages;    // [2]
+    uint64_t* acc_empty = acc_full + 2;             // [2] 4 epilogue warps arrive
+    uint64_t* w_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Ho = Hi >> 1, Wo = Wi >> 1;
+    const int tiles_x = (Wo + 7) / 8, tiles_y = (Ho + 15) / 16;
+    const int total_tiles = B * tiles_x * tiles_y;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kDownStages; ++s) { tc::mbar_init(a_full + s, 8); tc::mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 4); }
+        tc::mbar_init(w_full, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, 64);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {     // weights once per CTA
+            tc::mbar_expect_tx(w_full, Cfg::W_BYTES);
+            tc::bulk_g2s(wbuf, w, Cfg::W_BYTES, w_full);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
+            constexpr uint32_t a_hi = (uint32_t)((2 * kDownPitch * 16) >> 4) | (1u << 14);   // SBO: next output row = 2 input rows
+            constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+            const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + ((uint32_t)(kDownChunkBytes >> 4) << 16);
+            const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
+            tc::mbar_wait(w_full, 0);
+            int c = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int as = it & 1;
+                tc::mbar_wait(acc_empty + as, (uint32_t)(((it >> 1) & 1) ^ 1));
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 32);
+#pragma unroll 1
+                for (int ks = 0; ks < KS; ++ks, ++c) {
+                    const int s = c % kDownStages;
+                    tc::mbar_wait(a_full + s, (uint32_t)((c / kDownStages) & 1));
+                    tc::tc_fence_after();
+                    const uint32_t a_lo_s = a_lo0 + (uint32_t)(s * (kDownStageBytes >> 4));
+                    const uint32_t b_lo_s = b_lo0 + (uint32_t)(ks * 9 * 2 * NOUT);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        // parity plane (kx != 1), row shift ky, entry shift (kx == 2)
+                        const uint32_t aoff = (uint32_t)((kx != 1 ? (kDownParBytes >> 4) : 0) + ky * kDownPitch + (kx == 2 ? 1 : 0));
+                        const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + aoff);
+                        const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_s + (uint32_t)(tap * 2 * NOUT));
+                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, (ks | tap) != 0 ? 1u : 0u);
+                    }
+                    tc::umma_commit(a_empty + s);
+                }
+                tc::umma_commit(acc_full + as);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== loaders: 256 threads; task t = (K chunk t / 561, region position t % 561), lanes walk region columns =====
+        constexpr int POS = kDownRows * kDownCols;             // 561
+        constexpr int TASKS = 2 * POS;                          // per stage
+        constexpr int NT = (TASKS + 255) / 256;                 // 5
+        const int lt = tid - 128;
+        const size_t iplane = (size_t)Hi * Wi;
+        int c = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+            const int y_in0 = 2 * (ty * 16) - 1, x_in0 = 2 * (tx * 8) - 1;
+            const float* src_b = in + (size_t)b * CIN * iplane;
+            // geometry of this thread's tasks is the same for every K step of the tile
+            int goff[NT];       // element offset inside a channel plane, or -1 outside the map
+            int soff[NT];       // byte offset inside the stage, or -1 for "no task"
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const int t = lt + 256 * i;
+                soff[i] = -1; goff[i] = -1;
+                if (t < TASKS) {
+                    const int k = t / POS, pos = t - k * POS;
+                    const int r = pos / kDownCols, cc = pos - r * kDownCols;
+                    const int yi = y_in0 + r, xi = x_in0 + cc;
+                    soff[i] = k * kDownChunkBytes + ((cc & 1) ? 0 : kDownParBytes) + (r * kDownPitch + (cc >> 1)) * 16;
+                    if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) goff[i] = yi * Wi + xi;
+                }
+            }
+#pragma unroll 1
+            for (int ks = 0; ks < KS; ++ks, ++c) {
+                const int s = c % kDownStages;
+                float v[NT][8];
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const int k = (lt + 256 * i) / POS;
+                    const int ch0 = 16 * ks + 8 * k;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[i][j] = 0.f;
+                        if (goff[i] >= 0 && ch0 + j < CIN) v[i][j] = __ldg(src_b + (size_t)(ch0 + j) * iplane + goff[i]);
+                    }
+                }
+                tc::mbar_wait(a_empty + s, (uint32_t)(((c / kDownStages) & 1) ^ 1));
+                uint8_t* dst = abuf + s * kDownStageBytes;
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    if (soff[i] < 0) continue;
+                    __half2 h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i][2 * j], v[i][2 * j + 1]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                    u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                    *reinterpret_cast<uint4*>(dst + soff[i]) = u;
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(a_full + s);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue: TMEM -> fp16 chunk-plane o1h [B][kc][Ho][Wo][8] =====
+        const int q = warp & 3;
+        const int row = 4 * q + (lane >> 3), col = lane & 7;
+        const size_t oplane = (size_t)Ho * Wo;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+            const int y = ty * 16 + row, x = tx * 8 + col;
+            const int as = it & 1;
+            tc::mbar_wait(acc_full + as, (uint32_t)((it >> 1) & 1));
+            tc::tc_fence_after();
+            float v[NOUT];
+            const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * 32);
+            if constexpr (NOUT == 32) tc::tmem_ld32(t0, v); else tc::tmem_ld16(t0, v);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + as);
+            if (y < Ho && x < Wo) {
+#pragma unroll
+                for (int kc = 0; kc < NKC; ++kc) {
+                    __half2 h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[8 * kc + 2 * j], v[8 * kc + 2 * j + 1]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                    u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                    *reinterpret_cast<uint4*>(o1h + (((size_t)b * NKC + kc) * oplane + (size_t)y * Wo + x) * 8) = u;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 64);
+}
+
+}  // namespace espnet
