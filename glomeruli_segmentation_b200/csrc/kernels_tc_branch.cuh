@@ -19,8 +19,8 @@
 //   * MMA order per tile: K step outer, (branch, tap) inner -- stage s only needs the K chunks of step s, so the TMA
 //     of the next tile's first half overlaps the second half's MMAs.
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-//     warps 4..11 = epilogue: TMEM -> registers, HFF sums, residual + BN + PReLU, planar fp32 stores; warp e works on
-//     TMEM lanes 32*(e%4).. and on the accumulator column groups g = e/4 (mod 2).
+//     warp 3 = L2 prefetcher of the residual, warps 4..19 = epilogue: TMEM -> registers, HFF sums, residual + BN +
+//     PReLU, planar fp32 stores; warp e works on TMEM lanes 32*(e%4).. and on accumulator column group e/4.
 #pragma once
 #include "kernels_fp32.cuh"
 #include "tc_common.cuh"
@@ -34,8 +34,12 @@ constexpr int kTcBoxW = kTcTileW + 2 * kTcHalo2;     // 40
 constexpr int kTcBoxH = kTcTileH + 2 * kTcHalo2;     // 48
 constexpr int kTcPlane2 = kTcBoxH * kTcBoxW * 16;    // bytes of one K chunk plane of the box: 30720
 constexpr int kTcStage = 2 * kTcPlane2;              // one pipeline stage = 2 K chunks = one K = 16 MMA step: 61440
-constexpr int kTcThreads = 384;
+constexpr int kTcThreads = 640;   // 4 control warps + 16 epilogue warps
 constexpr int kTcAccStages = 3;
+#ifndef ESPNET_TC_PREFETCH_LEAD
+#define ESPNET_TC_PREFETCH_LEAD 3
+#endif
+constexpr int kTcPrefetchLead = ESPNET_TC_PREFETCH_LEAD;   // tiles the L2 prefetcher runs ahead of the epilogue
 
 struct BranchTcParams {
     const __half* w;        // [5][9][NKC][NOUT][8] fp16 (d1, d2, d4, d8, d16)
@@ -80,6 +84,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
     uint64_t* acc_full = bars + 5;    // [3]
     uint64_t* acc_empty = bars + 8;   // [3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint32_t* epi_done = tmem_slot + 1;   // tiles finished by epilogue warp 0 (throttle of the L2 prefetcher)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, W = p.W;
@@ -92,7 +97,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
         tc::mbar_init(a_full + 0, 1); tc::mbar_init(a_full + 1, 1);
         tc::mbar_init(a_empty + 0, 1); tc::mbar_init(a_empty + 1, 1);
         tc::mbar_init(w_full, 1);
-        for (int s = 0; s < kTcAccStages; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 8); }
+        for (int s = 0; s < kTcAccStages; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 16); }
+        *epi_done = 0;
         tc::mbar_fence_init();
         tc::tma_prefetch_desc(&tmap);
     }
@@ -167,11 +173,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                 tc::umma_commit(acc_full + as);             // accumulators of this tile complete
             }
         }
+    } else if (warp == 3) {
+        // ===== L2 prefetcher for the residual input: the epilogue's loads are the latency-bound part of this kernel
+        // (16 warps x 5*GW loads in flight per SM), so this otherwise idle warp pulls the residual tile of the tile
+        // kTcPrefetchLead ahead into L2: 128 channels x 16 rows x 32 B segments = 64 warp-wide prefetches per tile.
+        if (VAR != 0) {
+            const size_t plane = (size_t)H * W;
+            auto prefetch_tile = [&](int it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+                const int r = lane & 15, y = ty * kTcTileH + r, x = tx * kTcTileW;
+                if (y >= H) return;
+                const float* base = p.res + (size_t)b * C * plane + (size_t)y * W + x;
+#pragma unroll 4
+                for (int c = lane >> 4; c < C; c += 2)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)c * plane));
+            };
+            // Throttle on a monotonic progress counter written by the epilogue (an mbarrier can NOT be observed by a
+            // thread that may lag more than one phase behind: it would wait for a phase that never comes).
+            for (int it = 0; it < my_tiles; ++it) {
+                while (*reinterpret_cast<volatile uint32_t*>(epi_done) + (uint32_t)kTcPrefetchLead <= (uint32_t)it) __nanosleep(200);
+                prefetch_tile(it);
+            }
+        }
     } else if (warp >= 4) {
-        // ===== epilogue: 8 warps; thread <-> pixel (TMEM lane), so a warp touches 4 rows x 32 B per channel plane =====
+        // ===== epilogue: 16 warps; thread <-> pixel (TMEM lane), so a warp touches 4 rows x 32 B per channel plane.
+        // Warp e works on TMEM lanes 32*(e%4).. and on accumulator column group G = e/4 of every tile: columns
+        // [GW*G, GW*G + GW) of all five branches (GW = NOUT/4), i.e. up to 5*GW concat channels.  G is dispatched to a
+        // COMPILE-TIME constant so that which channels exist is known statically and the group is straight-line code.
+        // Per tile: all residual loads first (the epilogue is the HBM side of this kernel: 16 warps x 5*GW loads in
+        // flight per SM), then the accumulators: per branch one TMEM load, the HFF prefix sum add1..add4
+        // (Model.py:152-155,203-206), residual add BEFORE BN (Model.py:211-212), folded BN + PReLU, optional second BR.
         constexpr bool HAS_RES = VAR != 0, HAS_OUT = VAR != 2, HAS_OUT2 = VAR != 1;
-        constexpr int NG = NOUT / 8;                                   // groups of 8 accumulator columns
-        const int e = warp - 4, q = e & 3, gpar = e >> 2;
+        constexpr int GW = NOUT / 4;
+        const int e = warp - 4, q = e & 3, gsel = e >> 2;
         const int row = 4 * q + (lane >> 3), col = lane & 7;
         const size_t plane = (size_t)H * W;
         const uint32_t plane_b = (uint32_t)(plane * sizeof(float));   // host guarantees C * plane * 4 < 2^32
@@ -187,66 +222,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
             char* out2_b = HAS_OUT2 ? reinterpret_cast<char*>(p.out2 + ((size_t)b * p.C2 + p.c2_off) * plane + pix) : nullptr;
             const int as = it % kTcAccStages;
             const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * Cfg::ACC_COLS);
-            bool waited = false;
-
-            // Column group g = accumulator columns [8g, 8g+8) of all five branches.  The 40 residual loads of the group
-            // are issued BEFORE the accumulators are waited for (memory-level parallelism: the epilogue is the HBM
-            // side of this kernel), then 5 TMEM loads, the HFF prefix sums add1..add4 (Model.py:152-155,203-206) in 8
-            // registers, and per concat channel: residual add BEFORE BN (Model.py:211-212), folded BN + PReLU, optional
-            // second BR.  The g loop stays rolled: small code, nothing hoisted into spills.
-#pragma unroll 1
-            for (int g = gpar; g < NG; g += 2) {
-                const uint32_t goff = (uint32_t)(8 * g) * plane_b;
-                float rv[5][8];
+            auto group = [&](auto gtag) {
+                constexpr int G = decltype(gtag)::value;
+                float rv[5][GW];
+#pragma unroll
+                for (int br = 0; br < 5; ++br)
+#pragma unroll
+                    for (int jj = 0; jj < GW; ++jj) rv[br][jj] = 0.f;
+                if (HAS_RES && valid) {
+#pragma unroll
+                    for (int br = 0; br < 5; ++br) {
+                        const int ch0 = br == 0 ? 0 : CO1 + (br - 1) * CO;
+                        const int cnt = br == 0 ? CO1 : CO;
+#pragma unroll
+                        for (int jj = 0; jj < GW; ++jj)
+                            if (GW * G + jj < cnt)
+                                rv[br][jj] = __ldg(reinterpret_cast<const float*>(res_b + (uint64_t)plane_b * (uint32_t)(ch0 + GW * G + jj)));
+                    }
+                }
+                tc::mbar_wait(acc_full + as, (uint32_t)((it / kTcAccStages) & 1));
+                tc::tc_fence_after();
+                float run[GW];
 #pragma unroll
                 for (int br = 0; br < 5; ++br) {
                     const int ch0 = br == 0 ? 0 : CO1 + (br - 1) * CO;
                     const int cnt = br == 0 ? CO1 : CO;
+                    uint32_t r[GW];
+                    __syncwarp();    // tcgen05.ld is .sync.aligned: the lanes diverge on `valid` around the stores
+                    if constexpr (GW == 8) tc::tmem_ld8_nowait(t0 + (uint32_t)(br * NOUT + GW * G), r);
+                    else tc::tmem_ld4_nowait(t0 + (uint32_t)(br * NOUT + GW * G), r);
+                    tc::tmem_ld_wait();
+                    float o[GW], o2[GW];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        rv[br][jj] = 0.f;
-                        if (HAS_RES && valid && 8 * g + jj < cnt)
-                            rv[br][jj] = __ldg(reinterpret_cast<const float*>(res_b + goff + (uint64_t)plane_b * (uint32_t)(ch0 + jj)));
-                    }
-                }
-                if (!waited) {
-                    tc::mbar_wait(acc_full + as, (uint32_t)((it / kTcAccStages) & 1));
-                    tc::tc_fence_after();
-                    waited = true;
-                }
-                uint32_t r[5][8];
-                __syncwarp();    // tcgen05.ld is .sync.aligned: the lanes diverged on `valid` in the previous group
-#pragma unroll
-                for (int br = 0; br < 5; ++br) tc::tmem_ld8_nowait(t0 + (uint32_t)(br * NOUT + 8 * g), r[br]);
-                tc::tmem_ld_wait();
-                if (!valid) continue;
-                float run[8];
-#pragma unroll
-                for (int br = 0; br < 5; ++br) {
-                    const int ch0 = br == 0 ? 0 : CO1 + (br - 1) * CO;     // first concat channel of this slice
-                    const int cnt = br == 0 ? CO1 : CO;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const float d = __uint_as_float(r[br][jj]);
+                    for (int jj = 0; jj < GW; ++jj) {
+                        const float d = __uint_as_float(r[jj]);
                         run[jj] = br <= 1 ? d : run[jj] + d;
-                        if (8 * g + jj >= cnt) continue;
-                        const float4 q1 = sep4[ch0 + 8 * g + jj];
-                        const float o = bn_prelu(run[jj] + rv[br][jj], q1.x, q1.y, q1.z);
-                        if (HAS_OUT) *reinterpret_cast<float*>(out_b + goff + (uint64_t)plane_b * (uint32_t)(ch0 + jj)) = o;
-                        if (HAS_OUT2) {
-                            const float4 q2 = sep4[128 + ch0 + 8 * g + jj];
-                            *reinterpret_cast<float*>(out2_b + goff + (uint64_t)plane_b * (uint32_t)(ch0 + jj)) = bn_prelu(o, q2.x, q2.y, q2.z);
+                        o[jj] = 0.f; o2[jj] = 0.f;
+                        if (GW * G + jj < cnt) {
+                            const float4 q1 = sep4[ch0 + GW * G + jj];
+                            o[jj] = bn_prelu(run[jj] + rv[br][jj], q1.x, q1.y, q1.z);
+                            if (HAS_OUT2) {
+                                const float4 q2 = sep4[128 + ch0 + GW * G + jj];
+                                o2[jj] = bn_prelu(o[jj], q2.x, q2.y, q2.z);
+                            }
+                        }
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int jj = 0; jj < GW; ++jj) {
+                            if (GW * G + jj >= cnt) continue;
+                            if (HAS_OUT) *reinterpret_cast<float*>(out_b + (uint64_t)plane_b * (uint32_t)(ch0 + GW * G + jj)) = o[jj];
+                            if (HAS_OUT2) *reinterpret_cast<float*>(out2_b + (uint64_t)plane_b * (uint32_t)(ch0 + GW * G + jj)) = o2[jj];
                         }
                     }
                 }
-            }
-            if (!waited) {   // (cannot happen for NOUT >= 16, kept for safety: every warp must consume the phase)
-                tc::mbar_wait(acc_full + as, (uint32_t)((it / kTcAccStages) & 1));
-                tc::tc_fence_after();
-            }
+            };
+            if (gsel == 0) group(IntTag<0>());
+            else if (gsel == 1) group(IntTag<1>());
+            else if (gsel == 2) group(IntTag<2>());
+            else group(IntTag<3>());
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acc_empty + as);
+            if (lane == 0) {
+                tc::mbar_arrive(acc_empty + as);
+                if (e == 0) *reinterpret_cast<volatile uint32_t*>(epi_done) = (uint32_t)(it + 1);
+            }
         }
     }
     tc::tc_fence_before();
