@@ -224,6 +224,8 @@ def run_ours(args):
     if sd is not None:
         model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval().set_mode(args.mode)
+    if args.fp32_impl != "auto":
+        model.set_option("fp32_impl", 1 if args.fp32_impl == "tc3" else 0)
     ens = None
     if wl == "espnet_b256_ens5":
         models = [model]
@@ -232,7 +234,10 @@ def run_ours(args):
             sdk = load_weights(k, False)
             if sdk is not None:
                 mk.load_state_dict(sdk, strict=True)
-            models.append(mk.to(dev).eval().set_mode(args.mode))
+            mk = mk.to(dev).eval().set_mode(args.mode)
+            if args.fp32_impl != "auto":
+                mk.set_option("fp32_impl", 1 if args.fp32_impl == "tc3" else 0)
+            models.append(mk)
         ens = ESPNetEnsemble(models, [FOLD_MEAN_STD[k] for k in range(1, 6)])
 
     u8_host = torch.from_numpy(synth_u8(B, H, W, 1234 + rank)).pin_memory()
@@ -392,6 +397,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--mode", default="fp32", choices=["fp32", "f16tc"],
                     help="fp32: CUDA-core FMA path (1e-3 logit bar); f16tc: tcgen05 fp16-operand path (0.999 mask-agreement bar)")
+    ap.add_argument("--fp32-impl", default="auto", choices=["auto", "cuda", "tc3"],
+                    help="fp32 mode only: cuda = CUDA-core FMA kernels, tc3 = tcgen05 with 3-term fp16 operand splits (fp32-equivalent)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--single-mode", action="store_true", help="skip the second leg that times the other compute mode")
     args = ap.parse_args()

@@ -17,7 +17,6 @@
 #include "kernels_fp32.cuh"
 #include "kernels_fp32_tma.cuh"
 #include "kernels_tc.cuh"
-#include "kernels_tc_reduce.cuh"
 #include "kernels_tc_down.cuh"
 #include "kernels_wsi.cuh"
 
@@ -44,7 +43,8 @@ struct HostTensor {
 struct BlockW {
     size_t c1 = 0, d1 = 0, chain = 0, s = 0, t = 0, a = 0;
     size_t tc = 0;   // offset (bytes) into the fp16 blob for the tensor-core path: branch weights
-    size_t tc_c1 = 0;   // ... and the 1x1 reduce weights [CIN/8][NOUT][8] (ESP blocks only)
+    size_t tc_c1 = 0;   // ... and the c1 reduce weights (1x1: [CIN/8][NOUT][8]; 3x3 s2: [ks][tap][2][NOUT][8])
+    size_t tc3 = 0, tc3_c1 = 0;   // 3-term split copies (fp32-equivalent tensor-core path): branch [hi|lo][ks][br][tap][2][NOUT][8], 1x1 reduce [hi|lo][CIN/8][NOUT][8]
 };
 
 struct Packed {
@@ -84,6 +84,7 @@ struct espnet_handle {
     size_t nparams_h = 0;
     Packed pk;
     std::map<std::string, StageRef> stages;
+    int fp32_impl = 1;     // fp32 mode: 1 (default) = tensor cores with 3-term fp16 operand splits (fp32-equivalent), 0 = CUDA-core FMA kernels ("fp32_impl")
     int tc_reduce = 1;     // f16tc mode: 1 = 1x1 reduce on tensor cores, 0 = CUDA-core fp32 reduce rounded to fp16 ("tc_reduce")
     int branch_impl = 0;   // 0 auto, 1 per-thread global loads, 2 TMA-staged (espnet_set_option "branch_impl")
     // per-kernel CUDA-event timing (espnet_set_profiling)
@@ -278,6 +279,53 @@ struct Packer {
                     dst[((size_t)(c / 8) * nout + o) * 8 + (c % 8)] = bits;
                 }
         }
+        {   // 3-term fp16 split copies: w_hi = fp16(4 w), w_lo = fp16(4 w - w_hi)
+            auto split = [](float wv, uint16_t& hi, uint16_t& lo) {
+                const float sw = wv * 4.0f;
+                const __half h = __float2half_rn(sw);
+                const __half l = __float2half_rn(sw - __half2float(h));
+                std::memcpy(&hi, &h, 2); std::memcpy(&lo, &l, 2);
+            };
+            const int nkc = 2 * ((n + 15) / 16), ks_n = nkc / 2, nout = n1 <= 16 ? 16 : 32;
+            const size_t unit = (size_t)5 * 9 * 2 * nout * 8;           // halves per (K step, hi|lo)
+            while (blob_h.size() % 64) blob_h.push_back(0);
+            bw.tc3 = blob_h.size() * sizeof(uint16_t);
+            blob_h.resize(blob_h.size() + 2 * ks_n * unit, 0);
+            uint16_t* dst = blob_h.data() + bw.tc3 / sizeof(uint16_t);
+            const int dd[5] = {1, 2, 4, 8, 16};
+            for (int b = 0; b < 5; ++b) {
+                const int co_n = b == 0 ? n1 : n;
+                const HostTensor* w = get(key + ".d" + std::to_string(dd[b]) + ".conv.weight", {co_n, n, 3, 3});
+                if (!w) return false;
+                for (int t = 0; t < 9; ++t)
+                    for (int o = 0; o < co_n; ++o)
+                        for (int c = 0; c < n; ++c) {
+                            uint16_t hi, lo;
+                            split(w->data[((size_t)o * n + c) * 9 + t], hi, lo);
+                            const size_t idx = (size_t)(c / 16) * unit + ((((size_t)b * 9 + t) * 2 + (c % 16) / 8) * nout + o) * 8 + (c % 8);
+                            dst[idx] = hi;
+                            dst[(size_t)ks_n * unit + idx] = lo;
+                        }
+            }
+            if (!down) {
+                const int nout1 = 8 * nkc;
+                const HostTensor* w = get(key + ".c1.conv.weight", {n, cin, 1, 1});
+                if (!w) return false;
+                const size_t part = (size_t)(cin / 8) * nout1 * 8;
+                while (blob_h.size() % 64) blob_h.push_back(0);
+                bw.tc3_c1 = blob_h.size() * sizeof(uint16_t);
+                blob_h.resize(blob_h.size() + 2 * part, 0);
+                uint16_t* d1p = blob_h.data() + bw.tc3_c1 / sizeof(uint16_t);
+                for (int o = 0; o < n; ++o)
+                    for (int c = 0; c < cin; ++c) {
+                        uint16_t hi, lo;
+                        split(w->data[(size_t)o * cin + c], hi, lo);
+                        const size_t idx = ((size_t)(c / 8) * nout1 + o) * 8 + (c % 8);
+                        d1p[idx] = hi;
+                        d1p[part + idx] = lo;
+                    }
+            }
+        }
         const std::string bnk = down ? key + ".bn" : key + ".bn.bn";
         const std::string ak = down ? key + ".act.weight" : key + ".bn.act.weight";
         return bn(bnk, cout, bw.s, bw.t) && vec(ak, cout, bw.a);
@@ -296,7 +344,12 @@ Workspace layout(const espnet_t* h, int B, int H, int W) {
     w.out0cat = take((size_t)B * 19 * P2);
     {   // o1 rows are padded to a multiple of 4 floats so that the map can be a TMA tensor (16 B strides)
         const size_t p4 = (size_t)(H / 4) * (size_t)pad4(W / 4), p8 = (size_t)(H / 8) * (size_t)pad4(W / 8);
-        w.o1 = take((size_t)B * 12 * p4 > (size_t)B * 25 * p8 ? (size_t)B * 12 * p4 : (size_t)B * 25 * p8);
+        size_t need = (size_t)B * 12 * p4 > (size_t)B * 25 * p8 ? (size_t)B * 12 * p4 : (size_t)B * 25 * p8;
+        // fp16 chunk-plane hi / lo pair of the split tensor-core path: 2 x 16 ch x 2 B (level 2), 2 x 32 ch x 2 B (level 3) per pixel
+        const size_t split4 = (size_t)B * 16 * P4, split8 = (size_t)B * 32 * P8;
+        if (split4 > need) need = split4;
+        if (split8 > need) need = split8;
+        w.o1 = take(need);
     }
     w.l2a = take((size_t)B * 64 * P4);
     w.l2b = take((size_t)B * 64 * P4);
@@ -445,7 +498,7 @@ int make_o1h_map(espnet_t* h, CUtensorMap* map, const __half* o1h, int B, int NK
     return ESPNET_OK;
 }
 
-template <int CIN, int CO, int NKC>
+template <int CIN, int CO, int NKC, bool SPLIT = false>
 int run_reduce1x1_f16(espnet_t* h, const float* in, size_t w_off, __half* o1h, int B, int H, int W, cudaStream_t st) {
     const int HW = H * W;
     const size_t smem = (size_t)CIN * pad4(CO) * sizeof(float);
@@ -454,21 +507,21 @@ int run_reduce1x1_f16(espnet_t* h, const float* in, size_t w_off, __half* o1h, i
     const long long cap = 2LL * h->num_sms;
     if (ctas > cap) ctas = cap;
     { ProfScope _ps(h, CIN == 64 ? "reduce1x1_f16_l2" : "reduce1x1_f16_l3", st);
-      reduce1x1_f16_kernel<CIN, CO, NKC><<<(int)ctas, 256, smem, st>>>(in, h->dparams + w_off, o1h, B, HW); }
+      reduce1x1_f16_kernel<CIN, CO, NKC, SPLIT><<<(int)ctas, 256, smem, st>>>(in, h->dparams + w_off, o1h, B, HW); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
 }
 
-template <int CIN, int NOUT, int NKC>
+template <int CIN, int NOUT, int NKC, bool SPLIT = false>
 int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h, int B, int H, int W, cudaStream_t st) {
-    using Cfg = ReduceTcCfg<CIN, NOUT>;
+    using Cfg = ReduceTcCfg<CIN, NOUT, SPLIT>;
     const int HW = H * W;
-    int rc = set_smem(h, reduce1x1_tc_kernel<CIN, NOUT, NKC>, Cfg::SMEM);
+    int rc = set_smem(h, reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT>, Cfg::SMEM);
     if (rc) return rc;
     const int grid = grid_for(h, (long long)B * ((HW + 127) / 128));
-    { ProfScope _ps(h, CIN == 64 ? "reduce1x1_tc_l2" : "reduce1x1_tc_l3", st);
-      reduce1x1_tc_kernel<CIN, NOUT, NKC><<<grid, kRedThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + bw.tc_c1), o1h, B, HW); }
+    { ProfScope _ps(h, SPLIT ? (CIN == 64 ? "reduce1x1_tc3_l2" : "reduce1x1_tc3_l3") : (CIN == 64 ? "reduce1x1_tc_l2" : "reduce1x1_tc_l3"), st);
+      reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kRedThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1)), o1h, B, HW); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -488,25 +541,25 @@ int run_reduce3x3_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
     return ESPNET_OK;
 }
 
-template <int CIN, int CO, int NKC>
+template <int CIN, int CO, int NKC, bool SPLIT = false>
 int run_reduce3x3_f16(espnet_t* h, const float* in, size_t w_off, __half* o1h, int B, int Hi, int Wi, cudaStream_t st) {
     const size_t smem = ((size_t)9 * CIN + 4) * pad4(CO) * sizeof(float);
-    int rc = set_smem(h, reduce3x3s2_f16_kernel<CIN, CO, NKC>, smem);
+    int rc = set_smem(h, reduce3x3s2_f16_kernel<CIN, CO, NKC, SPLIT>, smem);
     if (rc) return rc;
     const int grid = grid_for(h, tile_items(B, Hi / 2, Wi / 2));
     { ProfScope _ps(h, CIN == 19 ? "reduce3x3s2_f16_l2" : "reduce3x3s2_f16_l3", st);
-      reduce3x3s2_f16_kernel<CIN, CO, NKC><<<grid, kHeavyThreads, smem, st>>>(in, h->dparams + w_off, o1h, B, Hi, Wi); }
+      reduce3x3s2_f16_kernel<CIN, CO, NKC, SPLIT><<<grid, kHeavyThreads, smem, st>>>(in, h->dparams + w_off, o1h, B, Hi, Wi); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
 }
 
-template <int NKC, int NOUT, int CO1, int CO>
+template <int NKC, int NOUT, int CO1, int CO, bool SPLIT = false>
 int run_branch_tc(espnet_t* h, const BlockW& bw, const __half* o1h, const float* res, float* out, float* out2, int C2, int c2_off,
                   size_t s2, size_t t2, size_t a2, int B, int H, int W, cudaStream_t st) {
-    using Cfg = BranchTcCfg<NKC, NOUT>;
+    using Cfg = BranchTcCfg<NKC, NOUT, SPLIT>;
     BranchTcParams p{};
-    p.w = reinterpret_cast<const __half*>(h->dparams_h + bw.tc);
+    p.w = reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3 : bw.tc));
     p.res = res;
     p.s = h->dparams + bw.s; p.t = h->dparams + bw.t; p.a = h->dparams + bw.a;
     p.out = out;
@@ -515,18 +568,18 @@ int run_branch_tc(espnet_t* h, const BlockW& bw, const __half* o1h, const float*
     p.B = B; p.H = H; p.W = W;
     const int var = res == nullptr ? 0 : (out != nullptr ? 1 : 2);
     if ((var == 0 && (!out || !out2)) || (var == 2 && !out2)) return fail(h, ESPNET_EINVAL, "run_branch_tc: unsupported output combination");
-    auto k0 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 0>;
-    auto k1 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 1>;
-    auto k2 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 2>;
+    auto k0 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 0, SPLIT>;
+    auto k1 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 1, SPLIT>;
+    auto k2 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 2, SPLIT>;
     auto kern = var == 0 ? k0 : (var == 1 ? k1 : k2);
     int rc = set_smem(h, kern, Cfg::SMEM);
     if (rc) return rc;
     CUtensorMap map;
-    rc = make_o1h_map(h, &map, o1h, B, NKC, H, W, kTcBoxW, kTcBoxH, 2);
+    rc = make_o1h_map(h, &map, o1h, SPLIT ? 2 * B : B, NKC, H, W, kTcBoxW, kTcBoxH, 2);
     if (rc) return rc;
     const long long tiles = (long long)B * ((H + kTcTileH - 1) / kTcTileH) * ((W + kTcTileW - 1) / kTcTileW);
     const int grid = grid_for(h, tiles);
-    { ProfScope _ps(h, NKC == 2 ? "esp_branch_tc_l2" : "esp_branch_tc_l3", st);
+    { ProfScope _ps(h, SPLIT ? (NKC == 2 ? "esp_branch_tc3_l2" : "esp_branch_tc3_l3") : (NKC == 2 ? "esp_branch_tc_l2" : "esp_branch_tc_l3"), st);
       kern<<<grid, kTcThreads, Cfg::SMEM, st>>>(map, p); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
@@ -679,6 +732,7 @@ int espnet_set_mode(espnet_t* h, int mode) {
 int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (!h || !key) return ESPNET_EINVAL;
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "fp32_impl") == 0 && value >= 0 && value <= 1) { h->fp32_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 1) { h->tc_reduce = value; return ESPNET_OK; }
     return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);
 }
@@ -820,6 +874,11 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
             if (r) return r;
             return run_branch_tc<2, 16, 16, 12>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
         }
+        if (h->fp32_impl == 1) {   // fp32-equivalent on tensor cores: 3-term fp16 operand splits, fp32 accumulation
+            r = down ? run_reduce3x3_f16<19, 12, 2, true>(h, in, bw.c1, o1h, B, H2, W2, st) : run_reduce1x1_tc<64, 16, 2, true>(h, in, bw, o1h, B, H4, W4, st);
+            if (r) return r;
+            return run_branch_tc<2, 16, 16, 12, true>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
+        }
         r = down ? run_reduce3x3<19, 12>(h, in, bw.c1, ws + L.o1, B, H2, W2, st) : run_reduce1x1<64, 12>(h, in, bw.c1, ws + L.o1, B, H4, W4, st);
         if (r) return r;
         return run_branch<12, 16, 12>(h, bw, ws + L.o1, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
@@ -831,6 +890,11 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
                      : (h->tc_reduce ? run_reduce1x1_tc<128, 32, 4>(h, in, bw, o1h, B, H8, W8, st) : run_reduce1x1_f16<128, 25, 4>(h, in, bw.c1, o1h, B, H8, W8, st));
             if (r) return r;
             return run_branch_tc<4, 32, 28, 25>(h, bw, o1h, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
+        }
+        if (h->fp32_impl == 1) {
+            r = down ? run_reduce3x3_f16<131, 25, 4, true>(h, in, bw.c1, o1h, B, H4, W4, st) : run_reduce1x1_tc<128, 32, 4, true>(h, in, bw, o1h, B, H8, W8, st);
+            if (r) return r;
+            return run_branch_tc<4, 32, 28, 25, true>(h, bw, o1h, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
         }
         r = down ? run_reduce3x3<131, 25>(h, in, bw.c1, ws + L.o1, B, H4, W4, st) : run_reduce1x1<128, 25>(h, in, bw.c1, ws + L.o1, B, H8, W8, st);
         if (r) return r;

@@ -11,6 +11,7 @@
 #include "kernels_fp32.cuh"
 #include "tc_common.cuh"
 #include "kernels_tc_branch.cuh"
+#include "kernels_tc_reduce.cuh"
 
 namespace espnet {
 
@@ -24,27 +25,17 @@ constexpr int kTcPlaneBytes = kTcBox * kTcBox * 16;
 // ------------------------------------------------------------------------------------------------
 // fp16 chunk-plane stores for the reduce kernels: o1h[((b*NKC + kc)*HW + pix)*8 + j] = half(acc[kc*8+j])
 // ------------------------------------------------------------------------------------------------
-template <int CO, int NKC>
-__device__ __forceinline__ void store_o1_f16(__half* __restrict__ o1h, int b, size_t HW, size_t pix, const float (&acc)[CO]) {
+// SPLIT: the hi / lo pair (fp16(a/4) and its fp16 remainder) as crops [0,B) and [B,2B) of one tensor (fp32-equivalent path)
+template <int CO, int NKC, bool SPLIT = false>
+__device__ __forceinline__ void store_o1_f16(__half* __restrict__ o1h, int B, int b, size_t HW, size_t pix, const float (&acc)[CO]) {
+    float v[NKC * 8];
 #pragma unroll
-    for (int kc = 0; kc < NKC; ++kc) {
-        __half2 h[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c0 = kc * 8 + 2 * j, c1 = c0 + 1;
-            const float v0 = c0 < CO ? acc[c0 < CO ? c0 : 0] : 0.f;
-            const float v1 = c1 < CO ? acc[c1 < CO ? c1 : 0] : 0.f;
-            h[j] = __floats2half2_rn(v0, v1);
-        }
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
-        u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
-        *reinterpret_cast<uint4*>(o1h + (((size_t)b * NKC + kc) * HW + pix) * 8) = u;
-    }
+    for (int c = 0; c < NKC * 8; ++c) v[c] = c < CO ? acc[c < CO ? c : 0] : 0.f;
+    store_o1_chunks<NKC * 8, NKC, SPLIT>(o1h, B, b, HW, pix, v);
 }
 
 // ESP reduce (Model.py:178,192): 1x1 conv CIN -> CO on CUDA cores in fp32, result rounded once to fp16.
-template <int CIN, int CO, int NKC>
+template <int CIN, int CO, int NKC, bool SPLIT>
 __global__ void __launch_bounds__(256) reduce1x1_f16_kernel(const float* __restrict__ in, const float* __restrict__ w /*[CIN][pad4(CO)]*/,
                                                             __half* __restrict__ o1h, int B, int HW) {
     constexpr int CP = pad4(CO);
@@ -89,12 +80,12 @@ __global__ void __launch_bounds__(256) reduce1x1_f16_kernel(const float* __restr
         }
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
-            if (ok[r]) store_o1_f16<CO, NKC>(o1h, b, (size_t)HW, (size_t)(p0 + 32 * r), acc[r]);
+            if (ok[r]) store_o1_f16<CO, NKC, SPLIT>(o1h, B, b, (size_t)HW, (size_t)(p0 + 32 * r), acc[r]);
     }
 }
 
 // DownSamplerB reduce (Model.py:135,145): 3x3 stride-2 conv CIN -> CO, fp32 CUDA cores, fp16 chunk-plane output.
-template <int CIN, int CO, int NKC>
+template <int CIN, int CO, int NKC, bool SPLIT>
 __global__ void __launch_bounds__(kHeavyThreads, 1) reduce3x3s2_f16_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                            __half* __restrict__ o1h, int B, int Hi, int Wi) {
     constexpr int CP = pad4(CO);
@@ -122,7 +113,7 @@ __global__ void __launch_bounds__(kHeavyThreads, 1) reduce3x3s2_f16_kernel(const
         if (x < Wo) {
 #pragma unroll
             for (int r = 0; r < kRows; ++r)
-                if (y0 + r < Ho) store_o1_f16<CO, NKC>(o1h, b, (size_t)Ho * Wo, (size_t)(y0 + r) * Wo + x, acc[r]);
+                if (y0 + r < Ho) store_o1_f16<CO, NKC, SPLIT>(o1h, B, b, (size_t)Ho * Wo, (size_t)(y0 + r) * Wo + x, acc[r]);
         }
     }
 }

@@ -52,11 +52,13 @@ struct BranchTcParams {
     int B, H, W;
 };
 
-template <int NKC, int NOUT>
+template <int NKC, int NOUT, bool SPLIT = false>
 struct BranchTcCfg {
     static constexpr int KS = NKC / 2;                            // K = 16 steps per tile
-    static constexpr int W_BRANCH = 9 * NKC * NOUT * 16;          // bytes of one branch's weights
-    static constexpr int W_BYTES = 5 * W_BRANCH;
+    static constexpr int W_BRANCH = 9 * NKC * NOUT * 16;          // bytes of one branch's weights (plain layout)
+    static constexpr int W_UNIT = 5 * 9 * 2 * NOUT * 16;          // split layout: all branches, one K step, hi OR lo
+    static constexpr bool W_STREAM = SPLIT && KS > 1;             // split weights do not fit: 2-unit ring, else resident
+    static constexpr int W_BYTES = SPLIT ? 2 * W_UNIT : 5 * W_BRANCH;
     static constexpr int ACC_COLS = 5 * NOUT;                     // TMEM columns per tile
     static constexpr int TMEM_COLS = (kTcAccStages * ACC_COLS <= 256) ? 256 : 512;
     static constexpr int EP_BYTES = 2 * 128 * 16;                 // two float4 tables of 128 channels
@@ -66,9 +68,17 @@ struct BranchTcCfg {
 
 // VAR: 0 = DownSamplerB (no residual, writes out and out2), 1 = ESP block (residual, out), 2 = last ESP block of a level
 // (residual, writes only the BR'd copy into the following concat buffer)
-template <int NKC, int NOUT, int CO1, int CO, int VAR>
+//
+// SPLIT = true is the fp32-equivalent variant (ESPNET_MODE_FP32 with fp32_impl = tensor cores): both operands are
+// 3-term fp16 splits, a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with a_hi = fp16(a/4), a_lo = fp16(a/4 - a_hi),
+// w_hi = fp16(4w), w_lo = fp16(4w - w_hi): 22-bit mantissa products, fp32 accumulation in TMEM.  o1 arrives as two
+// chunk-plane tensors (hi crops [0,B), lo crops [B,2B) of one tensor map); per K step the hi half-box goes to stage
+// 0 and the lo half-box to stage 1, and the weights [hi|lo][K step][branch][tap][2][NOUT][8] stream through a 2-unit
+// ring (unit 0 = W_hi(k), unit 1 = W_lo(k)) because hi + lo of all branches (180 KB) do not fit next to the boxes.
+// MMA order per K step: A_lo x W_hi, A_hi x W_hi, A_hi x W_lo -- 3x the MMAs of the plain variant.
+template <int NKC, int NOUT, int CO1, int CO, int VAR, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BranchTcParams p) {
-    using Cfg = BranchTcCfg<NKC, NOUT>;
+    using Cfg = BranchTcCfg<NKC, NOUT, SPLIT>;
     constexpr int C = CO1 + 4 * CO;
     constexpr int KS = Cfg::KS;
     static_assert(C <= 128 && CO1 <= NOUT && CO <= NOUT && (NOUT == 16 || NOUT == 32), "channel counts");
@@ -80,10 +90,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sep4) + Cfg::EP_BYTES);
     uint64_t* a_full = bars + 0;      // [2]
     uint64_t* a_empty = bars + 2;     // [2]
-    uint64_t* w_full = bars + 4;
-    uint64_t* acc_full = bars + 5;    // [3]
-    uint64_t* acc_empty = bars + 8;   // [3]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* w_full = bars + 4;      // [2] (plain variant: only [0])
+    uint64_t* w_empty = bars + 6;     // [2] (streamed split weights only)
+    uint64_t* acc_full = bars + 8;    // [3]
+    uint64_t* acc_empty = bars + 11;  // [3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     uint32_t* epi_done = tmem_slot + 1;   // tiles finished by epilogue warp 0 (throttle of the L2 prefetcher)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -96,7 +107,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
         if ((tc::smem_addr(abuf) & 127u) != 0) __trap();   // TMA destination alignment
         tc::mbar_init(a_full + 0, 1); tc::mbar_init(a_full + 1, 1);
         tc::mbar_init(a_empty + 0, 1); tc::mbar_init(a_empty + 1, 1);
-        tc::mbar_init(w_full, 1);
+        tc::mbar_init(w_full + 0, 1); tc::mbar_init(w_full + 1, 1);
+        tc::mbar_init(w_empty + 0, 1); tc::mbar_init(w_empty + 1, 1);
         for (int s = 0; s < kTcAccStages; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 16); }
         *epi_done = 0;
         tc::mbar_fence_init();
@@ -114,20 +126,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer: weights once, then one half-box (2 K chunks) per pipeline step =====
+        // ===== producer =====
         if (lane == 0) {
-            tc::mbar_expect_tx(w_full, Cfg::W_BYTES);
-            tc::bulk_g2s(wbuf, p.w, Cfg::W_BYTES, w_full);
-            int c = 0;   // chunk counter: chunk c of this CTA = (tile c / KS, K step c % KS), stage c & 1
-            for (int it = 0; it < my_tiles; ++it) {
-                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-                const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+            if constexpr (!SPLIT) {
+                // weights once, then one half-box (2 K chunks) per pipeline step
+                tc::mbar_expect_tx(w_full, Cfg::W_BYTES);
+                tc::bulk_g2s(wbuf, p.w, Cfg::W_BYTES, w_full);
+                int c = 0;   // chunk counter: chunk c of this CTA = (tile c / KS, K step c % KS), stage c & 1
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks, ++c) {
-                    const int s = c & 1;
-                    tc::mbar_wait(a_empty + s, (uint32_t)(((c >> 1) & 1) ^ 1));
-                    tc::mbar_expect_tx(a_full + s, kTcStage);
-                    tc::tma_load_4d(abuf + s * kTcStage, &tmap, a_full + s, 4 * (tx * kTcTileW - kTcHalo2), ty * kTcTileH - kTcHalo2, 2 * ks, b);
+                    for (int ks = 0; ks < KS; ++ks, ++c) {
+                        const int s = c & 1;
+                        tc::mbar_wait(a_empty + s, (uint32_t)(((c >> 1) & 1) ^ 1));
+                        tc::mbar_expect_tx(a_full + s, kTcStage);
+                        tc::tma_load_4d(abuf + s * kTcStage, &tmap, a_full + s, 4 * (tx * kTcTileW - kTcHalo2), ty * kTcTileH - kTcHalo2, 2 * ks, b);
+                    }
+                }
+            } else {
+                // per K step n: W_hi(k) -> unit 0, A_lo(k) -> stage 1, A_hi(k) -> stage 0, W_lo(k) -> unit 1 (the order in
+                // which the MMA issuer frees / needs them)
+                const uint8_t* wg = reinterpret_cast<const uint8_t*>(p.w);
+                int n = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+                    const int cx = 4 * (tx * kTcTileW - kTcHalo2), cy = ty * kTcTileH - kTcHalo2;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks, ++n) {
+                        const uint32_t par = (uint32_t)(n & 1);
+                        tc::mbar_wait(a_empty + 1, par ^ 1);
+                        tc::mbar_expect_tx(a_full + 1, kTcStage);
+                        tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 2 * ks, b + p.B);
+                        if (Cfg::W_STREAM || n == 0) {
+                            if (Cfg::W_STREAM) tc::mbar_wait(w_empty + 0, par ^ 1);
+                            tc::mbar_expect_tx(w_full + 0, Cfg::W_UNIT);
+                            tc::bulk_g2s(wbuf, wg + (size_t)ks * Cfg::W_UNIT, Cfg::W_UNIT, w_full + 0);
+                        }
+                        tc::mbar_wait(a_empty + 0, par ^ 1);
+                        tc::mbar_expect_tx(a_full + 0, kTcStage);
+                        tc::tma_load_4d(abuf, &tmap, a_full + 0, cx, cy, 2 * ks, b);
+                        if (Cfg::W_STREAM || n == 0) {
+                            if (Cfg::W_STREAM) tc::mbar_wait(w_empty + 1, par ^ 1);
+                            tc::mbar_expect_tx(w_full + 1, Cfg::W_UNIT);
+                            tc::bulk_g2s(wbuf + Cfg::W_UNIT, wg + (size_t)(KS + ks) * Cfg::W_UNIT, Cfg::W_UNIT, w_full + 1);
+                        }
+                    }
                 }
             }
         }
@@ -142,35 +187,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
             constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
             const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + (uint32_t)(kTcHalo2 * kTcBoxW + kTcHalo2) + ((uint32_t)(kTcPlane2 >> 4) << 16);
             const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
-            tc::mbar_wait(w_full, 0);
-            int c = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int as = it % kTcAccStages;
-                tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
-                const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks, ++c) {
-                    const int s = c & 1;
-                    tc::mbar_wait(a_full + s, (uint32_t)((c >> 1) & 1));
-                    tc::tc_fence_after();
-                    const uint32_t a_lo_s = a_lo0 + (uint32_t)(s * (kTcStage >> 4));
-                    const uint32_t b_lo_s = b_lo0 + (uint32_t)(2 * ks * NOUT);
+            // 45 MMAs: all branches and taps of one K step; a_lo_s = A stage, b_lo_s = weights of branch 0 / tap 0,
+            // b_br / b_tap = weight strides in 16 B units, fresh = first K step of the tile (overwrite the accumulators)
+            auto issue45 = [&](uint32_t a_lo_s, uint32_t b_lo_s, uint32_t b_br, uint32_t b_tap, uint32_t d_tile, bool fresh) {
 #pragma unroll 1
-                    for (int br = 0; br < 5; ++br) {
-                        const int d = 1 << br, dp = d * kTcBoxW;
-                        const uint32_t b_lo = b_lo_s + (uint32_t)(br * (Cfg::W_BRANCH >> 4));
-                        const uint32_t d_tmem = d_tile + (uint32_t)(br * NOUT);
+                for (int br = 0; br < 5; ++br) {
+                    const int d = 1 << br, dp = d * kTcBoxW;
+                    const uint32_t b_lo = b_lo_s + (uint32_t)br * b_br;
+                    const uint32_t d_tmem = d_tile + (uint32_t)(br * NOUT);
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int ky = tap / 3 - 1, kx = tap % 3 - 1;           // compile-time after unrolling
-                            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + (uint32_t)(ky * dp + kx * d));
-                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(tap * (NKC * NOUT)));
-                            tc::umma_f16(d_tmem, adesc, bdesc, idesc, (ks | tap) != 0 ? 1u : 0u);
-                        }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3 - 1, kx = tap % 3 - 1;           // compile-time after unrolling
+                        const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + (uint32_t)(ky * dp + kx * d));
+                        const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)tap * b_tap);
+                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, (fresh && tap == 0) ? 0u : 1u);
                     }
-                    tc::umma_commit(a_empty + s);           // this half-box is reusable once the MMAs above have read it
                 }
-                tc::umma_commit(acc_full + as);             // accumulators of this tile complete
+            };
+            if constexpr (!SPLIT) {
+                tc::mbar_wait(w_full, 0);
+                int c = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int as = it % kTcAccStages;
+                    tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
+                    const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks, ++c) {
+                        const int s = c & 1;
+                        tc::mbar_wait(a_full + s, (uint32_t)((c >> 1) & 1));
+                        tc::tc_fence_after();
+                        issue45(a_lo0 + (uint32_t)(s * (kTcStage >> 4)), b_lo0 + (uint32_t)(2 * ks * NOUT), (uint32_t)(Cfg::W_BRANCH >> 4),
+                                (uint32_t)(NKC * NOUT), d_tile, ks == 0);
+                        tc::umma_commit(a_empty + s);           // this half-box is reusable once the MMAs above have read it
+                    }
+                    tc::umma_commit(acc_full + as);             // accumulators of this tile complete
+                }
+            } else {
+                constexpr uint32_t BR = 9 * 2 * NOUT, TAP = 2 * NOUT;       // split weight layout strides (16 B units)
+                const uint32_t a_st0 = a_lo0, a_st1 = a_lo0 + (uint32_t)(kTcStage >> 4);
+                const uint32_t w_u0 = b_lo0, w_u1 = b_lo0 + (uint32_t)(Cfg::W_UNIT >> 4);
+                int n = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int as = it % kTcAccStages;
+                    tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
+                    const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks, ++n) {
+                        const uint32_t par = (uint32_t)(n & 1);
+                        // (1) A_lo x W_hi
+                        if (Cfg::W_STREAM || n == 0) tc::mbar_wait(w_full + 0, Cfg::W_STREAM ? par : 0u);
+                        tc::mbar_wait(a_full + 1, par);
+                        tc::tc_fence_after();
+                        issue45(a_st1, w_u0, BR, TAP, d_tile, ks == 0);
+                        tc::umma_commit(a_empty + 1);
+                        // (2) A_hi x W_hi
+                        tc::mbar_wait(a_full + 0, par);
+                        tc::tc_fence_after();
+                        issue45(a_st0, w_u0, BR, TAP, d_tile, false);
+                        if (Cfg::W_STREAM) tc::umma_commit(w_empty + 0);
+                        // (3) A_hi x W_lo
+                        if (Cfg::W_STREAM || n == 0) tc::mbar_wait(w_full + 1, Cfg::W_STREAM ? par : 0u);
+                        tc::tc_fence_after();
+                        issue45(a_st0, w_u1, BR, TAP, d_tile, false);
+                        tc::umma_commit(a_empty + 0);
+                        if (Cfg::W_STREAM) tc::umma_commit(w_empty + 1);
+                    }
+                    tc::umma_commit(acc_full + as);
+                }
             }
         }
     } else if (warp == 3) {

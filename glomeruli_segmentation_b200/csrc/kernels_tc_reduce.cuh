@@ -16,19 +16,56 @@ namespace espnet {
 
 constexpr int kRedThreads = 512;
 
-template <int CIN, int NOUT>
+// SPLIT: fp32-equivalent variant, both operands as 3-term fp16 splits (see kernels_tc_branch.cuh): the A stage holds
+// [hi planes | lo planes], the weights [hi | lo], three MMAs per K step, and the result is written as the hi / lo
+// chunk-plane pair (crops [0,B) and [B,2B) of one tensor) the split branch kernel reads.
+constexpr float kSplitScaleA = 0.25f;   // activations are stored as fp16(a/4) (+ remainder), weights as fp16(4w) (+ remainder)
+
+__device__ __forceinline__ void split_f16x2(float a, float b, __half2& hi, __half2& lo) {
+    const float sa = a * kSplitScaleA, sb = b * kSplitScaleA;
+    hi = __floats2half2_rn(sa, sb);
+    const float2 hf = __half22float2(hi);
+    lo = __floats2half2_rn(sa - hf.x, sb - hf.y);
+}
+
+template <int CIN, int NOUT, bool SPLIT = false>
 struct ReduceTcCfg {
     static constexpr int KC = CIN / 8;                 // input K chunks
-    static constexpr int A_STAGE = KC * 128 * 16;      // bytes
-    static constexpr int W_BYTES = KC * NOUT * 16;
+    static constexpr int A_PART = KC * 128 * 16;       // bytes of one (hi or lo) operand copy
+    static constexpr int A_STAGE = (SPLIT ? 2 : 1) * A_PART;
+    static constexpr int W_PART = KC * NOUT * 16;
+    static constexpr int W_BYTES = (SPLIT ? 2 : 1) * W_PART;
     static constexpr size_t SMEM = 1024 + 2 * (size_t)A_STAGE + W_BYTES + 256;
 };
 
-// w: [CIN/8][NOUT][8] fp16, element (kc, n, j) = W1[co = n][ci = 8 kc + j] (zero for n >= CO)
-template <int CIN, int NOUT, int NKC>
+// accumulator row (NOUT fp32) -> fp16 chunk-plane o1h [B][kc][HW][8], or the hi / lo pair [2B][kc][HW][8] when SPLIT
+template <int NOUT, int NKC, bool SPLIT>
+__device__ __forceinline__ void store_o1_chunks(__half* __restrict__ o1h, int B, int b, size_t HW, size_t pix, const float (&v)[NOUT]) {
+#pragma unroll
+    for (int kc = 0; kc < NKC; ++kc) {
+        __half2 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if constexpr (SPLIT) split_f16x2(v[8 * kc + 2 * j], v[8 * kc + 2 * j + 1], h[j], l[j]);
+            else h[j] = __floats2half2_rn(v[8 * kc + 2 * j], v[8 * kc + 2 * j + 1]);
+        }
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        *reinterpret_cast<uint4*>(o1h + (((size_t)b * NKC + kc) * HW + pix) * 8) = u;
+        if constexpr (SPLIT) {
+            u.x = *reinterpret_cast<uint32_t*>(&l[0]); u.y = *reinterpret_cast<uint32_t*>(&l[1]);
+            u.z = *reinterpret_cast<uint32_t*>(&l[2]); u.w = *reinterpret_cast<uint32_t*>(&l[3]);
+            *reinterpret_cast<uint4*>(o1h + (((size_t)(B + b) * NKC + kc) * HW + pix) * 8) = u;
+        }
+    }
+}
+
+// w: [CIN/8][NOUT][8] fp16 (SPLIT: hi copy then lo copy), element (kc, n, j) = W1[co = n][ci = 8 kc + j] (zero for n >= CO)
+template <int CIN, int NOUT, int NKC, bool SPLIT>
 __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const float* __restrict__ in, const __half* __restrict__ w,
                                                                       __half* __restrict__ o1h, int B, int HW) {
-    using Cfg = ReduceTcCfg<CIN, NOUT>;
+    using Cfg = ReduceTcCfg<CIN, NOUT, SPLIT>;
     constexpr int KC = Cfg::KC;
     static_assert(CIN % 16 == 0 && NKC * 8 == NOUT, "shapes");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -77,9 +114,13 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
                 const uint32_t d_tmem = tmem_base + (uint32_t)(s * 32);
 #pragma unroll
                 for (int ks = 0; ks < KC / 2; ++ks) {
-                    const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(s * (Cfg::A_STAGE >> 4) + 2 * ks * (2048 >> 4)));
-                    const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(2 * ks * NOUT));
-                    tc::umma_f16(d_tmem, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+                    const uint32_t al = a_lo0 + (uint32_t)(s * (Cfg::A_STAGE >> 4) + 2 * ks * (2048 >> 4));
+                    const uint32_t bl = b_lo0 + (uint32_t)(2 * ks * NOUT);
+                    tc::umma_f16(d_tmem, ((uint64_t)a_hi << 32) | al, ((uint64_t)b_hi << 32) | bl, idesc, ks != 0 ? 1u : 0u);
+                    if constexpr (SPLIT) {
+                        tc::umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (al + (uint32_t)(Cfg::A_PART >> 4)), ((uint64_t)b_hi << 32) | bl, idesc, 1u);   // lo x W_hi
+                        tc::umma_f16(d_tmem, ((uint64_t)a_hi << 32) | al, ((uint64_t)b_hi << 32) | (bl + (uint32_t)(Cfg::W_PART >> 4)), idesc, 1u);   // hi x W_lo
+                    }
                 }
                 tc::umma_commit(a_empty + s);
                 tc::umma_commit(acc_full + s);
@@ -106,13 +147,21 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
             tc::mbar_wait(a_empty + s, (uint32_t)(((it >> 1) & 1) ^ 1));
 #pragma unroll
             for (int k = 0; k < KC / 2; ++k) {
-                __half2 h[4];
+                __half2 h[4], l[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[k][2 * j], v[k][2 * j + 1]);
+                for (int j = 0; j < 4; ++j) {
+                    if constexpr (SPLIT) split_f16x2(v[k][2 * j], v[k][2 * j + 1], h[j], l[j]);
+                    else h[j] = __floats2half2_rn(v[k][2 * j], v[k][2 * j + 1]);
+                }
                 uint4 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
                 u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
                 *reinterpret_cast<uint4*>(dst + (kc0 + k) * 2048) = u;
+                if constexpr (SPLIT) {
+                    u.x = *reinterpret_cast<uint32_t*>(&l[0]); u.y = *reinterpret_cast<uint32_t*>(&l[1]);
+                    u.z = *reinterpret_cast<uint32_t*>(&l[2]); u.w = *reinterpret_cast<uint32_t*>(&l[3]);
+                    *reinterpret_cast<uint4*>(dst + Cfg::A_PART + (kc0 + k) * 2048) = u;
+                }
             }
             tc::fence_proxy_async();
             __syncwarp();
@@ -133,18 +182,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + s);
-            if (p < HW) {
-#pragma unroll
-                for (int kc = 0; kc < NKC; ++kc) {
-                    __half2 h[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[8 * kc + 2 * j], v[8 * kc + 2 * j + 1]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
-                    u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
-                    *reinterpret_cast<uint4*>(o1h + (((size_t)b * NKC + kc) * HW + p) * 8) = u;
-                }
-            }
+            if (p < HW) store_o1_chunks<NOUT, NKC, SPLIT>(o1h, B, b, (size_t)HW, (size_t)p, v);
         }
     }
     tc::tc_fence_before();

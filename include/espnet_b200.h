@@ -50,8 +50,11 @@ typedef struct {
 #define ESPNET_IN_U8_SLIDE 2    /* tiles read straight out of a resident u8 [SH,SW,3] slide at origins[B][2]   */
 
 /* compute modes */
-#define ESPNET_MODE_FP32 0      /* fp32 CUDA-core FMA everywhere: logits within 1e-3 of the reference          */
-#define ESPNET_MODE_F16TC 1     /* fp16 storage + tcgen05 (kind::f16, fp32 accumulate) ESP blocks: mask parity  */
+#define ESPNET_MODE_FP32 0      /* fp32-equivalent arithmetic, logits within 1e-3 of the reference.  Option "fp32_impl":
+                                   1 (default) = the contractions of the DownSampler / ESP blocks on tcgen05 with 3-term
+                                   fp16 operand splits (22-bit mantissa products, fp32 accumulation), everything else
+                                   fp32 FMA; 0 = fp32 CUDA-core FMA everywhere                                        */
+#define ESPNET_MODE_F16TC 1     /* single fp16 operands on tcgen05 (fp32 accumulate, fp32 storage): arg-max parity bar */
 
 /* what the network is: full ESPNet (Model.py:306) or ESPNet-C encoder only (Model.py:242) */
 #define ESPNET_NET_FULL 0
@@ -90,8 +93,8 @@ ESPNET_API const char* espnet_last_error(const espnet_t* h); /* h may be NULL: l
 ESPNET_API int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n);
 
 ESPNET_API int espnet_set_mode(espnet_t* h, int mode);            /* ESPNET_MODE_* ; default FP32 */
-/* Tuning knobs (never change results beyond fp32 re-association): "branch_impl" = 0 auto, 1 per-thread global
- * loads, 2 TMA-staged shared-memory halo tiles. */
+/* Options: "fp32_impl" (see ESPNET_MODE_FP32); "branch_impl" (CUDA-core fp32 branch kernel: 0 auto, 1 per-thread global
+ * loads, 2 TMA-staged shared-memory halo tiles); "tc_reduce" (F16TC mode: 1 = reduce convs on tensor cores, 0 = CUDA cores). */
 ESPNET_API int espnet_set_option(espnet_t* h, const char* key, int value);
 ESPNET_API size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W);
 

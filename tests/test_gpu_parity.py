@@ -108,13 +108,16 @@ def test_random_weights_and_ragged_shapes_against_oracle(classes, p, q, B, H, W)
     assert _maxabs(e(x.to(DEV)), eref) <= LOGIT_TOL * max(1.0, eref.abs().max().item() / 10.0)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("B,H,W", [(1, 8, 8), (2, 72, 40), (1, 264, 328), (3, 256, 256)])
-def test_both_branch_kernels_against_oracle(fold_sd, impl, B, H, W):
-    """branch_impl 1 = per-thread global loads, 2 = TMA-staged halo tiles; both must hit the fp32 bar on
-    ragged maps (level-3 maps down to 1x1 and widths that are not multiples of 4 or 32)."""
+def test_all_fp32_branch_implementations_against_oracle(fold_sd, impl, B, H, W):
+    """impl 0 = default (tcgen05, 3-term fp16 operand splits); CUDA-core kernels: 1 = per-thread global loads,
+    2 = TMA-staged halo tiles.  All must hit the fp32 bar on ragged maps (level-3 maps down to 1x1 and widths that
+    are not multiples of 4, 8 or 32)."""
     sd = fold_sd(1)
-    m = _model(sd).set_option("branch_impl", impl)
+    m = _model(sd)
+    if impl:
+        m.set_option("fp32_impl", 0).set_option("branch_impl", impl)
     x = torch.from_numpy(O.normalise_bgr_u8(O.synth_crops("D2", B, H, W, seed=H, sigma=3.0), *FOLD_MEAN_STD[1]))
     ref = O.espnet_forward(sd, x)
     y = m(x.to(DEV))

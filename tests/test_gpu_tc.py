@@ -86,3 +86,60 @@ def test_tc_mode_is_deterministic_and_batch_invariant(fold_sd):
     b = m.segment(big, mean, std)
     assert torch.equal(b[:3], a) and torch.equal(b[147:150], a)
     assert torch.equal(m.segment(big, mean, std), b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32-equivalent tensor-core path: ESPNET_MODE_FP32 with option fp32_impl = 1 (3-term fp16 operand splits, 22-bit
+# mantissa products, fp32 accumulation in TMEM).  It carries the SAME bar as the CUDA-core fp32 path: logits within
+# 1e-3 max-abs of the reference (north_star).
+# ---------------------------------------------------------------------------------------------------------------
+LOGIT_TOL = 1e-3
+
+
+def _model_split(sd, classes=5, p=2, q=8):
+    m = ESPNet(classes, p, q)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval().set_mode("fp32").set_option("fp32_impl", 1)
+
+
+@pytest.mark.parametrize("fold", [1, 3])
+def test_split_path_matches_reference_golden(golden, fold_sd, fold):
+    m = _model_split(fold_sd(fold))
+    x = torch.from_numpy(golden["small_x_fold%d" % fold]).to(DEV)
+    y = m(x)
+    err = (y.cpu() - torch.from_numpy(golden["small_logits_fold%d" % fold])).abs().max().item()
+    assert err <= LOGIT_TOL, err
+    mask = y.max(1)[1].byte().cpu().numpy()
+    assert (mask == golden["small_mask_fold%d" % fold]).mean() >= 0.9999
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 8), (2, 72, 40), (1, 264, 328), (2, 512, 512)])
+@pytest.mark.parametrize("fold", [1, 3, 5])
+def test_split_path_logits_within_fp32_bar(fold_sd, fold, B, H, W):
+    sd = fold_sd(fold)
+    mean, std = FOLD_MEAN_STD[fold]
+    kind = "D1" if H == 512 else "D2"
+    u8 = O.synth_crops(kind, B, H, W, seed=7 * H + fold, sigma=3.0)
+    ref = O.espnet_forward(sd, torch.from_numpy(O.normalise_bgr_u8(u8, mean, std)))
+    m = _model_split(sd)
+    lg = torch.empty((B, 5, H, W), device=DEV)
+    mask = m.segment(torch.from_numpy(u8).to(DEV), mean, std, logits=lg)
+    err = (lg.cpu() - ref).abs().max().item()
+    assert err <= LOGIT_TOL, err
+    assert (mask.cpu().numpy() == O.argmax_mask(ref)).mean() >= 0.9999
+
+
+def test_split_path_multi_tile_per_cta_and_determinism(fold_sd):
+    """Many tiles per persistent CTA (pipeline wrap-around of every mbarrier ring) and run-to-run bit equality."""
+    sd = fold_sd(1)
+    mean, std = FOLD_MEAN_STD[1]
+    u8 = torch.from_numpy(O.synth_crops("D1", 3, 256, 256, seed=3)).to(DEV)
+    m32 = _model(sd, "fp32")
+    m = _model_split(sd)
+    la, lb = torch.empty((3, 5, 256, 256), device=DEV), torch.empty((150, 5, 256, 256), device=DEV)
+    m32.segment(u8, mean, std, logits=la)
+    big = u8.repeat(50, 1, 1, 1)
+    mb = m.segment(big, mean, std, logits=lb)
+    assert (lb[:3] - la).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(lb[147:150], lb[:3])
+    assert torch.equal(m.segment(big, mean, std), mb)
