@@ -175,16 +175,23 @@ def kernel_roofline(name, per_launch_ms, B, hbm_peak, peak_src):
     P4, P8 = 128 * 128, 64 * 64
     alg = {"esp_branch_l3": B * (25 + 128 + 128) * P8 * 4, "esp_branch_l2": B * (12 + 64 + 64) * P4 * 4,
            # tensor-core mode: o1 is fp16 padded to 32 / 16 channels, residual and output stay fp32
-           "esp_branch_tc_l3": B * (32 * 2 + 128 * 4 + 128 * 4) * P8, "esp_branch_tc_l2": B * (16 * 2 + 64 * 4 + 64 * 4) * P4}.get(name)
+           "esp_branch_tc_l3": B * (32 * 2 + 128 * 4 + 128 * 4) * P8, "esp_branch_tc_l2": B * (16 * 2 + 64 * 4 + 64 * 4) * P4,
+           # fp32-equivalent split mode: o1 is the fp16 hi + lo pair
+           "esp_branch_tc3_l3": B * (2 * 32 * 2 + 128 * 4 + 128 * 4) * P8, "esp_branch_tc3_l2": B * (2 * 16 * 2 + 64 * 4 + 64 * 4) * P4}.get(name)
     flops = {"esp_branch_l3": B * P8 * 2 * 9 * 25 * 128, "esp_branch_l2": B * P4 * 2 * 9 * 12 * 64,
-             "esp_branch_tc_l3": B * P8 * 2 * 9 * 25 * 128, "esp_branch_tc_l2": B * P4 * 2 * 9 * 12 * 64}.get(name)
+             "esp_branch_tc_l3": B * P8 * 2 * 9 * 25 * 128, "esp_branch_tc_l2": B * P4 * 2 * 9 * 12 * 64,
+             "esp_branch_tc3_l3": B * P8 * 2 * 9 * 25 * 128, "esp_branch_tc3_l2": B * P4 * 2 * 9 * 12 * 64}.get(name)
     if alg is None:
         return None
     ach = alg / (per_launch_ms * 1e-3) / 1e9
     roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
             "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg}
     tf = flops / (per_launch_ms * 1e-3) / 1e12
-    if "_tc_" in name:
+    if "_tc3_" in name:
+        roof["note"] = ("fp32-equivalent mode: the contraction runs on tcgen05 as 3 fp16 MMAs per product term set (3-term operand splits); "
+                        "the kernel is bounded by HBM (SURVEY.md 8(d)); tensor TFLOP/s below count the useful fp32-equivalent FLOPs once")
+        roof["tensor"] = {"achieved_tflops_useful": tf, "mma_flops_issued_factor": 3 * (32 * 32) / (25.0 * 26.6)}
+    elif "_tc_" in name:
         roof["note"] = "tcgen05 mode: the contraction runs on tensor cores, the kernel is bounded by HBM (SURVEY.md 8(d))"
         roof["tensor"] = {"achieved_tflops_useful": tf}
     else:
@@ -262,12 +269,14 @@ def run_ours(args):
             model._engine.forward(x_dev, _lib.IN_F32_NCHW, B, H, W, logits=logits, mask=mask_dev)
             return logits
 
+    pipe = model.host_pipeline(B, H, W, mean, std, depth=2) if ens is None else None
+
     def step_e2e():
+        if pipe is not None:     # public streaming API: H2D / kernels / D2H of consecutive batches overlap
+            pipe.submit(u8_host, mask_host)
+            return
         d = u8_host.to(dev, non_blocking=True)
-        if ens is not None:
-            mk = ens.segment(d)
-        else:
-            mk = model.segment(d, mean, std, out=mask_dev)
+        mk = ens.segment(d)
         mask_host.copy_(mk, non_blocking=True)
 
     def barrier():
@@ -275,12 +284,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, join=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        if join is not None:
+            join(True)          # side streams start after e0
         for _ in range(steps):
             fn()
+        if join is not None:
+            join(False)         # current stream waits for the side streams before e1
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -302,9 +315,22 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
+    def join_pipe(start):
+        if pipe is None:
+            return
+        cur = torch.cuda.current_stream(dev)
+        if start:
+            for st in (pipe.s_in, pipe.s_run, pipe.s_out):
+                st.wait_stream(cur)
+        else:
+            for st in (pipe.s_in, pipe.s_run, pipe.s_out):
+                cur.wait_stream(st)
+
     for _ in range(max(args.warmup, 3)):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    if pipe is not None:
+        pipe.drain()
+    ms_e2e = timed(step_e2e, args.steps, join_pipe)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     # per-kernel share of the step (CUDA events on the launching stream, same inputs, separate pass)
@@ -346,7 +372,7 @@ def run_ours(args):
 
     hbm_peak, peak_src = peaks()
     if other is not None:
-        for kname in ("esp_branch_tc_l3", "esp_branch_tc_l2", "esp_branch_l3", "esp_branch_l2"):
+        for kname in ("esp_branch_tc_l3", "esp_branch_tc_l2", "esp_branch_tc3_l3", "esp_branch_tc3_l2", "esp_branch_l3", "esp_branch_l2"):
             if kname in other["kernels"]:
                 kk = other["kernels"][kname]
                 other.setdefault("rooflines", {})[kname] = kernel_roofline(kname, kk["ms_per_step"] / kk["launches_per_step"], B, hbm_peak, peak_src)
@@ -369,7 +395,7 @@ def run_ours(args):
         "config": dict(workload_config(wl, B), mode=args.mode),
         "mpx_per_s": value * H * W / 1e6,
         "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(u8_host.numel()), "d2h_bytes_per_step": int(mask_host.numel()),
-                "ms_per_step": ms_e2e / args.steps, "api": "model.segment(u8 crops) -> u8 class map, pinned host buffers"},
+                "ms_per_step": ms_e2e / args.steps, "api": "model.host_pipeline(...).submit(pinned host u8 crops, pinned host u8 masks): H2D, fused normalise + forward + arg-max, D2H every step, 3 streams x 2 device slots"},
         "gpu_launches": launches,
         "roofline": roof,
         "kernels": kernels,

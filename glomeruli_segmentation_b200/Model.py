@@ -321,6 +321,10 @@ class _KernelBacked(nn.Module):
                     slide_hw=(slide_u8.shape[0], slide_u8.shape[1]), mask=out)
         return out
 
+    def host_pipeline(self, B: int, H: int, W: int, mean, std, depth: int = 2) -> "HostPipeline":
+        """Pipelined host-to-host segmentation of a stream of batches (see HostPipeline)."""
+        return HostPipeline(self, B, H, W, mean, std, depth)
+
     def segment_host(self, crops_u8: np.ndarray, mean, std) -> np.ndarray:
         """Host buffers in, host masks out (the per-crop loop of VisualizeResults_iou.py:100-129, batched);
         H2D, kernels, D2H and the sync all happen inside the C call `espnet_segment_host`."""
@@ -333,6 +337,49 @@ class _KernelBacked(nn.Module):
         _lib.check(_lib.lib().espnet_segment_host(eng.handle, crops_u8.ctypes.data, B, H, W, m, s, out.ctypes.data),
                    eng.handle, "espnet_segment_host")
         return out
+
+
+class HostPipeline:
+    """Streaming form of the per-crop loop of VisualizeResults_iou.py:100-129 for batches that live in (pinned) HOST
+    memory: `submit(crops_u8_host, masks_host)` enqueues H2D -> fused normalise + forward + arg-max -> D2H on three CUDA
+    streams with `depth` device slots, so the copies of one batch overlap the kernels of its neighbours; `drain()` waits
+    for everything submitted.  Host tensors must stay alive (and should be pinned) until drained."""
+
+    def __init__(self, model: "_KernelBacked", B: int, H: int, W: int, mean, std, depth: int = 2):
+        dev = model._param_device()
+        self.model, self.mean, self.std, self.shape, self.depth = model, mean, std, (B, H, W), depth
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.d_in = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.d_mask = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.n = 0
+        model._ready(dev)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(torch.cuda.current_stream(dev))
+
+    def submit(self, crops_u8_host: torch.Tensor, masks_host: torch.Tensor):
+        k = self.n % self.depth
+        if self.n >= self.depth:
+            self.s_in.wait_event(self.ev_run[k])      # slot's previous forward has consumed its input
+            self.s_run.wait_event(self.ev_out[k])     # ... and its mask has left the device
+        with torch.cuda.stream(self.s_in):
+            self.d_in[k].copy_(crops_u8_host, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.ev_in[k])
+            self.model.segment(self.d_in[k], self.mean, self.std, out=self.d_mask[k])
+            self.ev_run[k].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_run[k])
+            masks_host.copy_(self.d_mask[k], non_blocking=True)
+            self.ev_out[k].record(self.s_out)
+        self.n += 1
+
+    def drain(self):
+        self.s_out.synchronize()
+        self.s_run.synchronize()
 
 
 class ESPNet_Encoder(_KernelBacked):

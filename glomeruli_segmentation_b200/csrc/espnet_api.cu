@@ -307,6 +307,25 @@ struct Packer {
                             dst[(size_t)ks_n * unit + idx] = lo;
                         }
             }
+            if (down) {    // 3x3 stride-2 reduce: [hi|lo][ks][tap][2][NOUT][8]
+                const int nout1 = 8 * nkc, ks1 = (cin + 15) / 16;
+                const HostTensor* w = get(key + ".c1.conv.weight", {n, cin, 3, 3});
+                if (!w) return false;
+                const size_t part = (size_t)ks1 * 9 * 2 * nout1 * 8;
+                while (blob_h.size() % 64) blob_h.push_back(0);
+                bw.tc3_c1 = blob_h.size() * sizeof(uint16_t);
+                blob_h.resize(blob_h.size() + 2 * part, 0);
+                uint16_t* d1p = blob_h.data() + bw.tc3_c1 / sizeof(uint16_t);
+                for (int o = 0; o < n; ++o)
+                    for (int c = 0; c < cin; ++c)
+                        for (int t = 0; t < 9; ++t) {
+                            uint16_t hi, lo;
+                            split(w->data[((size_t)o * cin + c) * 9 + t], hi, lo);
+                            const size_t idx = (((((size_t)(c / 16) * 9 + t) * 2 + (c % 16) / 8) * nout1 + o) * 8) + (c % 8);
+                            d1p[idx] = hi;
+                            d1p[part + idx] = lo;
+                        }
+            }
             if (!down) {
                 const int nout1 = 8 * nkc;
                 const HostTensor* w = get(key + ".c1.conv.weight", {n, cin, 1, 1});
@@ -527,15 +546,15 @@ int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
     return ESPNET_OK;
 }
 
-template <int CIN, int NOUT, int NKC>
+template <int CIN, int NOUT, int NKC, bool SPLIT = false>
 int run_reduce3x3_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h, int B, int Hi, int Wi, cudaStream_t st) {
-    using Cfg = DownTcCfg<CIN, NOUT>;
-    int rc = set_smem(h, reduce3x3s2_tc_kernel<CIN, NOUT, NKC>, Cfg::SMEM);
+    using Cfg = DownTcCfg<CIN, NOUT, SPLIT>;
+    int rc = set_smem(h, reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT>, Cfg::SMEM);
     if (rc) return rc;
     const int Ho = Hi / 2, Wo = Wi / 2;
     const int grid = grid_for(h, (long long)B * ((Ho + 15) / 16) * ((Wo + 7) / 8));
-    { ProfScope _ps(h, CIN == 19 ? "reduce3x3s2_tc_l2" : "reduce3x3s2_tc_l3", st);
-      reduce3x3s2_tc_kernel<CIN, NOUT, NKC><<<grid, kDownThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + bw.tc_c1), o1h, B, Hi, Wi); }
+    { ProfScope _ps(h, SPLIT ? (CIN == 19 ? "reduce3x3s2_tc3_l2" : "reduce3x3s2_tc3_l3") : (CIN == 19 ? "reduce3x3s2_tc_l2" : "reduce3x3s2_tc_l3"), st);
+      reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1)), o1h, B, Hi, Wi); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -733,7 +752,7 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (!h || !key) return ESPNET_EINVAL;
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "fp32_impl") == 0 && value >= 0 && value <= 1) { h->fp32_impl = value; return ESPNET_OK; }
-    if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 1) { h->tc_reduce = value; return ESPNET_OK; }
+    if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 2) { h->tc_reduce = value; return ESPNET_OK; }
     return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);
 }
 
@@ -875,7 +894,9 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
             return run_branch_tc<2, 16, 16, 12>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
         }
         if (h->fp32_impl == 1) {   // fp32-equivalent on tensor cores: 3-term fp16 operand splits, fp32 accumulation
-            r = down ? run_reduce3x3_f16<19, 12, 2, true>(h, in, bw.c1, o1h, B, H2, W2, st) : run_reduce1x1_tc<64, 16, 2, true>(h, in, bw, o1h, B, H4, W4, st);
+            // (19 input channels fill 19/32 of the MMA K and the region loader dominates: the CUDA-core fp32 reduce is faster here)
+            r = down ? (h->tc_reduce == 2 ? run_reduce3x3_tc<19, 16, 2, true>(h, in, bw, o1h, B, H2, W2, st) : run_reduce3x3_f16<19, 12, 2, true>(h, in, bw.c1, o1h, B, H2, W2, st))
+                     : run_reduce1x1_tc<64, 16, 2, true>(h, in, bw, o1h, B, H4, W4, st);
             if (r) return r;
             return run_branch_tc<2, 16, 16, 12, true>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
         }
@@ -892,7 +913,8 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
             return run_branch_tc<4, 32, 28, 25>(h, bw, o1h, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
         }
         if (h->fp32_impl == 1) {
-            r = down ? run_reduce3x3_f16<131, 25, 4, true>(h, in, bw.c1, o1h, B, H4, W4, st) : run_reduce1x1_tc<128, 32, 4, true>(h, in, bw, o1h, B, H8, W8, st);
+            r = down ? (h->tc_reduce ? run_reduce3x3_tc<131, 32, 4, true>(h, in, bw, o1h, B, H4, W4, st) : run_reduce3x3_f16<131, 25, 4, true>(h, in, bw.c1, o1h, B, H4, W4, st))
+                     : run_reduce1x1_tc<128, 32, 4, true>(h, in, bw, o1h, B, H8, W8, st);
             if (r) return r;
             return run_branch_tc<4, 32, 28, 25, true>(h, bw, o1h, down ? nullptr : in, out, out2, 256, c2_off, pk.b3_s, pk.b3_t, pk.b3_a, B, H8, W8, st);
         }

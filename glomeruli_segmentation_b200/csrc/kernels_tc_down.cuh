@@ -14,6 +14,7 @@
 #pragma once
 #include "kernels_fp32.cuh"
 #include "tc_common.cuh"
+#include "kernels_tc_reduce.cuh"
 
 namespace espnet {
 
@@ -22,25 +23,33 @@ constexpr int kDownRows = 33, kDownCols = 17, kDownPitch = 9;
 constexpr int kDownParBytes = kDownRows * kDownPitch * 16;      // one parity plane of one K chunk: 4752
 constexpr int kDownChunkBytes = 2 * kDownParBytes;              // 9504
 constexpr int kDownStageBytes = 2 * kDownChunkBytes;            // 19008: two K chunks = one K = 16 step
-constexpr int kDownStages = 4;
 
-template <int CIN, int NOUT>
+// SPLIT = fp32-equivalent variant (3-term fp16 operand splits, see kernels_tc_branch.cuh): a stage holds the hi and lo
+// copies of the region AND the hi / lo weights of its K step (hi + lo of all K steps, 162 KB at level 3, cannot stay
+// resident), streamed by a producer thread with cp.async.bulk; 3 MMAs per tap.
+template <int CIN, int NOUT, bool SPLIT = false>
 struct DownTcCfg {
     static constexpr int KS = (CIN + 15) / 16;                  // K = 16 steps
-    static constexpr int W_BYTES = KS * 9 * 2 * NOUT * 16;      // [ks][tap][2 chunks][NOUT][8] fp16
-    static constexpr size_t SMEM = 1024 + (size_t)kDownStages * kDownStageBytes + W_BYTES + 256;
+    static constexpr int WK = 9 * 2 * NOUT * 16;                // weights of one K step: [tap][2 chunks][NOUT][8] fp16
+    static constexpr int W_PART = KS * WK;                      // one (hi or lo) copy of all K steps
+    static constexpr int W_RESIDENT = SPLIT ? 0 : W_PART;
+    static constexpr int STAGES = SPLIT ? 3 : 4;
+    static constexpr int STAGE_BYTES = SPLIT ? 2 * kDownStageBytes + 2 * WK : kDownStageBytes;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + W_RESIDENT + 256;
 };
 
-template <int CIN, int NOUT, int NKC>
+template <int CIN, int NOUT, int NKC, bool SPLIT>
 __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const float* __restrict__ in, const __half* __restrict__ w,
                                                                         __half* __restrict__ o1h, int B, int Hi, int Wi) {
-    using Cfg = DownTcCfg<CIN, NOUT>;
+    using Cfg = DownTcCfg<CIN, NOUT, SPLIT>;
     constexpr int KS = Cfg::KS;
+    constexpr int kDownStages = Cfg::STAGES;
+    constexpr int STAGE = Cfg::STAGE_BYTES;
     static_assert(NKC * 8 == NOUT, "shapes");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* abuf = smem_raw;
-    uint8_t* wbuf = abuf + kDownStages * kDownStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + Cfg::W_BYTES);
+    uint8_t* wbuf = abuf + kDownStages * STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + Cfg::W_RESIDENT);
     uint64_t* a_full = bars + 0;                    // [4] 8 loader warps arrive
     uint64_t* a_empty = bars + kDownStages;         // [4] MMA commit
     uint64_t* acc_full = bars + 2 * kDownStages;    // [2]
@@ -55,7 +64,7 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
     const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < kDownStages; ++s) { tc::mbar_init(a_full + s, 8); tc::mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < kDownStages; ++s) { tc::mbar_init(a_full + s, SPLIT ? 9 : 8); tc::mbar_init(a_empty + s, 1); }   // 8 loader warps (+ the weight producer)
         for (int s = 0; s < 2; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 4); }
         tc::mbar_init(w_full, 1);
         tc::mbar_fence_init();
@@ -67,9 +76,23 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {     // weights once per CTA
-            tc::mbar_expect_tx(w_full, Cfg::W_BYTES);
-            tc::bulk_g2s(wbuf, w, Cfg::W_BYTES, w_full);
+        if (lane == 0) {
+            if constexpr (!SPLIT) {     // weights once per CTA
+                tc::mbar_expect_tx(w_full, Cfg::W_PART);
+                tc::bulk_g2s(wbuf, w, Cfg::W_PART, w_full);
+            } else {                    // hi / lo weights of every K step into its stage
+                const uint8_t* wg = reinterpret_cast<const uint8_t*>(w);
+                int c = 0;
+                for (int it = 0; it < my_tiles; ++it)
+                    for (int ks = 0; ks < KS; ++ks, ++c) {
+                        const int s = c % kDownStages;
+                        tc::mbar_wait(a_empty + s, (uint32_t)(((c / kDownStages) & 1) ^ 1));
+                        uint8_t* dst = abuf + s * STAGE + 2 * kDownStageBytes;
+                        tc::mbar_expect_tx(a_full + s, 2 * Cfg::WK);
+                        tc::bulk_g2s(dst, wg + (size_t)ks * Cfg::WK, Cfg::WK, a_full + s);
+                        tc::bulk_g2s(dst + Cfg::WK, wg + (size_t)Cfg::W_PART + (size_t)ks * Cfg::WK, Cfg::WK, a_full + s);
+                    }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -78,8 +101,8 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
             constexpr uint32_t a_hi = (uint32_t)((2 * kDownPitch * 16) >> 4) | (1u << 14);   // SBO: next output row = 2 input rows
             constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
             const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + ((uint32_t)(kDownChunkBytes >> 4) << 16);
-            const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
-            tc::mbar_wait(w_full, 0);
+            const uint32_t b_lo0 = (tc::smem_addr(SPLIT ? abuf : wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
+            if constexpr (!SPLIT) tc::mbar_wait(w_full, 0);
             int c = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int as = it & 1;
@@ -90,8 +113,9 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
                     const int s = c % kDownStages;
                     tc::mbar_wait(a_full + s, (uint32_t)((c / kDownStages) & 1));
                     tc::tc_fence_after();
-                    const uint32_t a_lo_s = a_lo0 + (uint32_t)(s * (kDownStageBytes >> 4));
-                    const uint32_t b_lo_s = b_lo0 + (uint32_t)(ks * 9 * 2 * NOUT);
+                    const uint32_t a_lo_s = a_lo0 + (uint32_t)(s * (STAGE >> 4));
+                    // plain: resident weights of K step ks; split: the stage's own [W_hi | W_lo] behind the two region copies
+                    const uint32_t b_lo_s = SPLIT ? b_lo0 + (uint32_t)((s * STAGE + 2 * kDownStageBytes) >> 4) : b_lo0 + (uint32_t)(ks * 9 * 2 * NOUT);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int ky = tap / 3, kx = tap % 3;
@@ -100,6 +124,10 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
                         const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + aoff);
                         const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_s + (uint32_t)(tap * 2 * NOUT));
                         tc::umma_f16(d_tmem, adesc, bdesc, idesc, (ks | tap) != 0 ? 1u : 0u);
+                        if constexpr (SPLIT) {
+                            tc::umma_f16(d_tmem, adesc + (uint64_t)(kDownStageBytes >> 4), bdesc, idesc, 1u);     // A_lo x W_hi
+                            tc::umma_f16(d_tmem, adesc, bdesc + (uint64_t)(Cfg::WK >> 4), idesc, 1u);            // A_hi x W_lo
+                        }
                     }
                     tc::umma_commit(a_empty + s);
                 }
@@ -149,17 +177,25 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
                     }
                 }
                 tc::mbar_wait(a_empty + s, (uint32_t)(((c / kDownStages) & 1) ^ 1));
-                uint8_t* dst = abuf + s * kDownStageBytes;
+                uint8_t* dst = abuf + s * STAGE;
 #pragma unroll
                 for (int i = 0; i < NT; ++i) {
                     if (soff[i] < 0) continue;
-                    __half2 h[4];
+                    __half2 h[4], l[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i][2 * j], v[i][2 * j + 1]);
+                    for (int j = 0; j < 4; ++j) {
+                        if constexpr (SPLIT) split_f16x2(v[i][2 * j], v[i][2 * j + 1], h[j], l[j]);
+                        else h[j] = __floats2half2_rn(v[i][2 * j], v[i][2 * j + 1]);
+                    }
                     uint4 u;
                     u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
                     u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
                     *reinterpret_cast<uint4*>(dst + soff[i]) = u;
+                    if constexpr (SPLIT) {
+                        u.x = *reinterpret_cast<uint32_t*>(&l[0]); u.y = *reinterpret_cast<uint32_t*>(&l[1]);
+                        u.z = *reinterpret_cast<uint32_t*>(&l[2]); u.w = *reinterpret_cast<uint32_t*>(&l[3]);
+                        *reinterpret_cast<uint4*>(dst + kDownStageBytes + soff[i]) = u;
+                    }
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
@@ -184,18 +220,7 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + as);
-            if (y < Ho && x < Wo) {
-#pragma unroll
-                for (int kc = 0; kc < NKC; ++kc) {
-                    __half2 h[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[8 * kc + 2 * j], v[8 * kc + 2 * j + 1]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
-                    u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
-                    *reinterpret_cast<uint4*>(o1h + (((size_t)b * NKC + kc) * oplane + (size_t)y * Wo + x) * 8) = u;
-                }
-            }
+            if (y < Ho && x < Wo) store_o1_chunks<NOUT, NKC, SPLIT>(o1h, B, b, oplane, (size_t)y * Wo + x, v);
         }
     }
     tc::tc_fence_before();
