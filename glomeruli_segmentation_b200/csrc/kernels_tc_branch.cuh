@@ -18,7 +18,7 @@
 //     runs while TMA and the tensor core work on tiles i+1 and i+2.
 //   * MMA order per tile: K step outer, (branch, tap) inner -- stage s only needs the K chunks of step s, so the TMA
 //     of the next tile's first half overlaps the second half's MMAs.
-//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane of the converged warp), warp 2 = TMEM allocator,
 //     warp 3 = L2 prefetcher of the residual, warps 4..19 = epilogue: TMEM -> registers, HFF sums, residual + BN +
 //     PReLU, planar fp32 stores; warp e works on TMEM lanes 32*(e%4).. and on accumulator column group e/4.
 #pragma once
@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the control flow converged, one elected lane issues =====
+        {
             constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
             // Descriptors as (hi, lo) words: hi = SBO | version is constant per operand, lo = start>>4 | LBO<<12 and
             // every window shift / tap is an ADD on lo in 16 B units.  One thread issues everything, so the per-MMA
@@ -188,21 +188,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
             const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + (uint32_t)(kTcHalo2 * kTcBoxW + kTcHalo2) + ((uint32_t)(kTcPlane2 >> 4) << 16);
             const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
             // 45 MMAs: all branches and taps of one K step; a_lo_s = A stage, b_lo_s = weights of branch 0 / tap 0,
-            // b_br / b_tap = weight strides in 16 B units, fresh = first K step of the tile (overwrite the accumulators)
-            auto issue45 = [&](uint32_t a_lo_s, uint32_t b_lo_s, uint32_t b_br, uint32_t b_tap, uint32_t d_tile, bool fresh) {
+            // b_br / b_tap = weight strides in 16 B units, fresh = first K step of the tile (overwrite the accumulators);
+            // afterwards up to three mbarriers receive the completion of everything issued so far (tcgen05.commit).
+            auto issue45 = [&](uint32_t a_lo_s, uint32_t b_lo_s, uint32_t b_br, uint32_t b_tap, uint32_t d_tile, bool fresh,
+                               uint64_t* c0, uint64_t* c1, uint64_t* c2) {
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
 #pragma unroll 1
-                for (int br = 0; br < 5; ++br) {
-                    const int d = 1 << br, dp = d * kTcBoxW;
-                    const uint32_t b_lo = b_lo_s + (uint32_t)br * b_br;
-                    const uint32_t d_tmem = d_tile + (uint32_t)(br * NOUT);
+                    for (int br = 0; br < 5; ++br) {
+                        const int d = 1 << br, dp = d * kTcBoxW;
+                        const uint32_t b_lo = b_lo_s + (uint32_t)br * b_br;
+                        const uint32_t d_tmem = d_tile + (uint32_t)(br * NOUT);
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int ky = tap / 3 - 1, kx = tap % 3 - 1;           // compile-time after unrolling
-                        const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + (uint32_t)(ky * dp + kx * d));
-                        const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)tap * b_tap);
-                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, (fresh && tap == 0) ? 0u : 1u);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3 - 1, kx = tap % 3 - 1;           // compile-time after unrolling
+                            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + (uint32_t)(ky * dp + kx * d));
+                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)tap * b_tap);
+                            tc::umma_f16(d_tmem, adesc, bdesc, idesc, (fresh && tap == 0) ? 0u : 1u);
+                        }
                     }
+                    if (c0) tc::umma_commit(c0);
+                    if (c1) tc::umma_commit(c1);
+                    if (c2) tc::umma_commit(c2);
                 }
+                __syncwarp();
             };
             if constexpr (!SPLIT) {
                 tc::mbar_wait(w_full, 0);
@@ -215,12 +224,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                     for (int ks = 0; ks < KS; ++ks, ++c) {
                         const int s = c & 1;
                         tc::mbar_wait(a_full + s, (uint32_t)((c >> 1) & 1));
-                        tc::tc_fence_after();
+                        __syncwarp();
+                        // the half-box is reusable once these MMAs have read it; after the last K step the tile is complete
                         issue45(a_lo0 + (uint32_t)(s * (kTcStage >> 4)), b_lo0 + (uint32_t)(2 * ks * NOUT), (uint32_t)(Cfg::W_BRANCH >> 4),
-                                (uint32_t)(NKC * NOUT), d_tile, ks == 0);
-                        tc::umma_commit(a_empty + s);           // this half-box is reusable once the MMAs above have read it
+                                (uint32_t)(NKC * NOUT), d_tile, ks == 0, a_empty + s, ks == KS - 1 ? acc_full + as : nullptr, nullptr);
                     }
-                    tc::umma_commit(acc_full + as);             // accumulators of this tile complete
                 }
             } else {
                 constexpr uint32_t BR = 9 * 2 * NOUT, TAP = 2 * NOUT;       // split weight layout strides (16 B units)
@@ -237,22 +245,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                         // (1) A_lo x W_hi
                         if (Cfg::W_STREAM || n == 0) tc::mbar_wait(w_full + 0, Cfg::W_STREAM ? par : 0u);
                         tc::mbar_wait(a_full + 1, par);
-                        tc::tc_fence_after();
-                        issue45(a_st1, w_u0, BR, TAP, d_tile, ks == 0);
-                        tc::umma_commit(a_empty + 1);
+                        __syncwarp();
+                        issue45(a_st1, w_u0, BR, TAP, d_tile, ks == 0, a_empty + 1, nullptr, nullptr);
                         // (2) A_hi x W_hi
                         tc::mbar_wait(a_full + 0, par);
-                        tc::tc_fence_after();
-                        issue45(a_st0, w_u0, BR, TAP, d_tile, false);
-                        if (Cfg::W_STREAM) tc::umma_commit(w_empty + 0);
+                        __syncwarp();
+                        issue45(a_st0, w_u0, BR, TAP, d_tile, false, Cfg::W_STREAM ? w_empty + 0 : nullptr, nullptr, nullptr);
                         // (3) A_hi x W_lo
                         if (Cfg::W_STREAM || n == 0) tc::mbar_wait(w_full + 1, Cfg::W_STREAM ? par : 0u);
-                        tc::tc_fence_after();
-                        issue45(a_st0, w_u1, BR, TAP, d_tile, false);
-                        tc::umma_commit(a_empty + 0);
-                        if (Cfg::W_STREAM) tc::umma_commit(w_empty + 1);
+                        __syncwarp();
+                        issue45(a_st0, w_u1, BR, TAP, d_tile, false, a_empty + 0, Cfg::W_STREAM ? w_empty + 1 : nullptr,
+                                ks == KS - 1 ? acc_full + as : nullptr);
                     }
-                    tc::umma_commit(acc_full + as);
                 }
             }
         }

@@ -127,6 +127,19 @@ __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// true in exactly one (always the same) lane of a CONVERGED warp.  tcgen05.mma / tcgen05.commit issued under this
+// predicate compile to a single UTCHMMA / UTCBAR; issued by "lane 0 of a diverged warp" ptxas wraps every one of them in
+// an ELECT ... BRA.U.ANY loop (measured: ~70 cycles per MMA instead of ~30).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- UMMA --------------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
