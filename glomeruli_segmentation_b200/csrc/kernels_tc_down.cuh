@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: converged warp, one elected lane issues (tc_common.cuh: elect_one) =====
+        {
             constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
             constexpr uint32_t a_hi = (uint32_t)((2 * kDownPitch * 16) >> 4) | (1u << 14);   // SBO: next output row = 2 input rows
             constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
@@ -112,10 +112,12 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
                 for (int ks = 0; ks < KS; ++ks, ++c) {
                     const int s = c % kDownStages;
                     tc::mbar_wait(a_full + s, (uint32_t)((c / kDownStages) & 1));
+                    __syncwarp();
                     tc::tc_fence_after();
                     const uint32_t a_lo_s = a_lo0 + (uint32_t)(s * (STAGE >> 4));
                     // plain: resident weights of K step ks; split: the stage's own [W_hi | W_lo] behind the two region copies
                     const uint32_t b_lo_s = SPLIT ? b_lo0 + (uint32_t)((s * STAGE + 2 * kDownStageBytes) >> 4) : b_lo0 + (uint32_t)(ks * 9 * 2 * NOUT);
+                    if (tc::elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int ky = tap / 3, kx = tap % 3;
@@ -130,76 +132,86 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
                         }
                     }
                     tc::umma_commit(a_empty + s);
+                    if (ks == KS - 1) tc::umma_commit(acc_full + as);
+                    }
+                    __syncwarp();
                 }
-                tc::umma_commit(acc_full + as);
             }
         }
     } else if (warp >= 4 && warp < 12) {
-        // ===== loaders: 256 threads; task t = (K chunk t / 561, region position t % 561), lanes walk region columns =====
+        // ===== loaders: 256 threads; task t = (K chunk t / 561, region position t % 561), lanes walk region columns.
+        // The global loads of chunk c+1 (next K step, possibly of the next tile) are issued BEFORE chunk c is converted
+        // and stored (register double buffer): the loaders are the HBM side of this kernel and were latency-bound. =====
         constexpr int POS = kDownRows * kDownCols;             // 561
         constexpr int TASKS = 2 * POS;                          // per stage
         constexpr int NT = (TASKS + 255) / 256;                 // 5
         const int lt = tid - 128;
         const size_t iplane = (size_t)Hi * Wi;
-        int c = 0;
-        for (int it = 0; it < my_tiles; ++it) {
+        int rr[NT], cq[NT], kk[NT], soff[NT];                   // task geometry inside the region: tile independent
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int t = lt + 256 * i;
+            soff[i] = -1; rr[i] = 0; cq[i] = 0; kk[i] = 0;
+            if (t < TASKS) {
+                const int k = t / POS, pos = t - k * POS;
+                const int r = pos / kDownCols, cc = pos - r * kDownCols;
+                rr[i] = r; cq[i] = cc; kk[i] = k;
+                soff[i] = k * kDownChunkBytes + ((cc & 1) ? 0 : kDownParBytes) + (r * kDownPitch + (cc >> 1)) * 16;
+            }
+        }
+        const int total = my_tiles * KS;
+        auto issue = [&](int c, float (&v)[NT][8]) {
+            const int it = c / KS, ks = c - it * KS;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
             const int y_in0 = 2 * (ty * 16) - 1, x_in0 = 2 * (tx * 8) - 1;
             const float* src_b = in + (size_t)b * CIN * iplane;
-            // geometry of this thread's tasks is the same for every K step of the tile
-            int goff[NT];       // element offset inside a channel plane, or -1 outside the map
-            int soff[NT];       // byte offset inside the stage, or -1 for "no task"
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
-                const int t = lt + 256 * i;
-                soff[i] = -1; goff[i] = -1;
-                if (t < TASKS) {
-                    const int k = t / POS, pos = t - k * POS;
-                    const int r = pos / kDownCols, cc = pos - r * kDownCols;
-                    const int yi = y_in0 + r, xi = x_in0 + cc;
-                    soff[i] = k * kDownChunkBytes + ((cc & 1) ? 0 : kDownParBytes) + (r * kDownPitch + (cc >> 1)) * 16;
-                    if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) goff[i] = yi * Wi + xi;
+                const int yi = y_in0 + rr[i], xi = x_in0 + cq[i];
+                const bool inb = soff[i] >= 0 && yi >= 0 && yi < Hi && xi >= 0 && xi < Wi;
+                const int ch0 = 16 * ks + 8 * kk[i];
+                const float* sp = src_b + (size_t)ch0 * iplane + (inb ? yi * Wi + xi : 0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[i][j] = (inb && ch0 + j < CIN) ? __ldg(sp + (size_t)j * iplane) : 0.f;
+            }
+        };
+        auto store = [&](int c, const float (&v)[NT][8]) {
+            const int s = c % kDownStages;
+            tc::mbar_wait(a_empty + s, (uint32_t)(((c / kDownStages) & 1) ^ 1));
+            uint8_t* dst = abuf + s * STAGE;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                if (soff[i] < 0) continue;
+                __half2 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if constexpr (SPLIT) split_f16x2(v[i][2 * j], v[i][2 * j + 1], h[j], l[j]);
+                    else h[j] = __floats2half2_rn(v[i][2 * j], v[i][2 * j + 1]);
+                }
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                *reinterpret_cast<uint4*>(dst + soff[i]) = u;
+                if constexpr (SPLIT) {
+                    u.x = *reinterpret_cast<uint32_t*>(&l[0]); u.y = *reinterpret_cast<uint32_t*>(&l[1]);
+                    u.z = *reinterpret_cast<uint32_t*>(&l[2]); u.w = *reinterpret_cast<uint32_t*>(&l[3]);
+                    *reinterpret_cast<uint4*>(dst + kDownStageBytes + soff[i]) = u;
                 }
             }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(a_full + s);
+        };
+        float va[NT][8], vb[NT][8];
+        if (total > 0) issue(0, va);
 #pragma unroll 1
-            for (int ks = 0; ks < KS; ++ks, ++c) {
-                const int s = c % kDownStages;
-                float v[NT][8];
-#pragma unroll
-                for (int i = 0; i < NT; ++i) {
-                    const int k = (lt + 256 * i) / POS;
-                    const int ch0 = 16 * ks + 8 * k;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        v[i][j] = 0.f;
-                        if (goff[i] >= 0 && ch0 + j < CIN) v[i][j] = __ldg(src_b + (size_t)(ch0 + j) * iplane + goff[i]);
-                    }
-                }
-                tc::mbar_wait(a_empty + s, (uint32_t)(((c / kDownStages) & 1) ^ 1));
-                uint8_t* dst = abuf + s * STAGE;
-#pragma unroll
-                for (int i = 0; i < NT; ++i) {
-                    if (soff[i] < 0) continue;
-                    __half2 h[4], l[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if constexpr (SPLIT) split_f16x2(v[i][2 * j], v[i][2 * j + 1], h[j], l[j]);
-                        else h[j] = __floats2half2_rn(v[i][2 * j], v[i][2 * j + 1]);
-                    }
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
-                    u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
-                    *reinterpret_cast<uint4*>(dst + soff[i]) = u;
-                    if constexpr (SPLIT) {
-                        u.x = *reinterpret_cast<uint32_t*>(&l[0]); u.y = *reinterpret_cast<uint32_t*>(&l[1]);
-                        u.z = *reinterpret_cast<uint32_t*>(&l[2]); u.w = *reinterpret_cast<uint32_t*>(&l[3]);
-                        *reinterpret_cast<uint4*>(dst + kDownStageBytes + soff[i]) = u;
-                    }
-                }
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(a_full + s);
+        for (int c = 0; c < total; c += 2) {
+            if (c + 1 < total) issue(c + 1, vb);
+            store(c, va);
+            if (c + 1 < total) {
+                if (c + 2 < total) issue(c + 2, va);
+                store(c + 1, vb);
             }
         }
     } else if (warp >= 12) {

@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: converged warp, one elected lane issues (tc_common.cuh: elect_one) =====
+        {
             constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
             constexpr uint32_t a_hi = (uint32_t)(128 >> 4) | (1u << 14);
             constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
@@ -110,8 +110,10 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
                 const int s = it & 1;
                 tc::mbar_wait(acc_empty + s, (uint32_t)(((it >> 1) & 1) ^ 1));
                 tc::mbar_wait(a_full + s, (uint32_t)((it >> 1) & 1));
+                __syncwarp();
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(s * 32);
+                if (tc::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < KC / 2; ++ks) {
                     const uint32_t al = a_lo0 + (uint32_t)(s * (Cfg::A_STAGE >> 4) + 2 * ks * (2048 >> 4));
@@ -124,6 +126,8 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
                 }
                 tc::umma_commit(a_empty + s);
                 tc::umma_commit(acc_full + s);
+                }
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 12) {
