@@ -6,5 +6,6 @@ from . import _lib  # noqa: F401
 from .Model import ESPNet, ESPNet_Encoder, ESPNetEnsemble, HostPipeline, FOLD_MEAN_STD  # noqa: F401
 from .IOUEval import iouEval  # noqa: F401
 from . import wsi  # noqa: F401
+from . import frontend  # noqa: F401
 
 __version__ = "0.1.0"

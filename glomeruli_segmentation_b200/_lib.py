@@ -50,6 +50,15 @@ SYMBOLS = {
     "espnet_ds8_lut": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "espnet_downsample_lut": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "espnet_confusion_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
+    "espnet_bilinear_lut": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "espnet_nearest_lut": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "espnet_preprocess_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "espnet_resize_nearest_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "espnet_palette_overlay": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "espnet_render_ds8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "espnet_class_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "espnet_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "espnet_launch_count": (C.c_ulonglong, []),
     "espnet_version": (C.c_int, []),

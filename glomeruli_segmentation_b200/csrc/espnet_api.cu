@@ -19,6 +19,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_tc_down.cuh"
 #include "kernels_wsi.cuh"
+#include "kernels_frontend.cuh"
 
 using namespace espnet;
 
@@ -1180,6 +1181,93 @@ int espnet_downsample_lut(const uint8_t* level0, int slide_h, int slide_w, uint8
     if (gx > 64) gx = 64;
     dim3 grid(gx, ds_h);
     downsample_lut_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(level0, slide_w, ds, ds_h, ds_w, ysrc_dev, xsrc_dev);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+// ---------------------------------------------------------------------------------- front-end / render
+// cv2.resize INTER_LINEAR source coordinates (OpenCV's generic resizeLinear): fx = (float)((d + 0.5) * scale - 0.5),
+// sx = floor(fx), fx -= sx, clamped at both ends; scale = 1 / ((double)dst / src).
+int espnet_bilinear_lut(int src_len, int dst_len, int32_t* idx, float* wgt) {
+    if (!idx || !wgt || src_len <= 0 || dst_len <= 0) return ESPNET_EINVAL;
+    const double scale = 1.0 / ((double)dst_len / (double)src_len);
+    for (int d = 0; d < dst_len; ++d) {
+        float fx = (float)(((double)d + 0.5) * scale - 0.5);
+        int sx = (int)std::floor(fx);
+        fx -= (float)sx;
+        if (sx < 0) { fx = 0.f; sx = 0; }
+        if (sx >= src_len - 1) { fx = 0.f; sx = src_len - 1; }
+        idx[d] = sx;
+        wgt[d] = fx;
+    }
+    return ESPNET_OK;
+}
+
+// cv2.resize INTER_NEAREST source index: min(floor(d * (src / dst)), src - 1)
+int espnet_nearest_lut(int src_len, int dst_len, int32_t* idx) {
+    if (!idx || src_len <= 0 || dst_len <= 0) return ESPNET_EINVAL;
+    const double scale = (double)src_len / (double)dst_len;
+    for (int d = 0; d < dst_len; ++d) {
+        int s = (int)std::floor((double)d * scale);
+        idx[d] = s > src_len - 1 ? src_len - 1 : s;
+    }
+    return ESPNET_OK;
+}
+
+int espnet_preprocess_resize(const uint8_t* crops, int B, int h, int w, const float mean[3], const float std_[3], const int32_t* xs_dev,
+                             const float* xf_dev, const int32_t* ys_dev, const float* yf_dev, float* out, int H, int W, void* stream) {
+    if (!crops || !mean || !std_ || !xs_dev || !xf_dev || !ys_dev || !yf_dev || !out || B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535)
+        return ESPNET_EINVAL;
+    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    preprocess_resize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(crops, B, h, w, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2], xs_dev,
+                                                                    xf_dev, ys_dev, yf_dev, out, H, W);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+int espnet_resize_nearest_u8(const uint8_t* src, int B, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* ysrc_dev,
+                             const int32_t* xsrc_dev, void* stream) {
+    if (!src || !dst || !ysrc_dev || !xsrc_dev || B <= 0 || sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0 || B > 65535 || dh > 65535) return ESPNET_EINVAL;
+    int gx = (dw + 255) / 256;
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, dh, B);
+    resize_nearest_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, B, sh, sw, dst, dh, dw, ysrc_dev, xsrc_dev);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+int espnet_palette_overlay(const uint8_t* img, const uint8_t* label, size_t npix, const uint8_t* palette_dev, int n_pal, uint8_t* color_out,
+                           uint8_t* overlay_out, void* stream) {
+    if (!label || !palette_dev || n_pal <= 0 || n_pal > 256 || (!color_out && !overlay_out) || (overlay_out && !img)) return ESPNET_EINVAL;
+    if (npix == 0) return ESPNET_OK;
+    size_t g = (npix + 256 * 8 - 1) / (256 * 8);
+    if (g > 4736) g = 4736;
+    palette_overlay_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(img, label, npix, palette_dev, n_pal, color_out, overlay_out);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+int espnet_render_ds8(const uint8_t* slide, const uint8_t* label, int slide_h, int slide_w, const uint8_t* palette_dev, int n_pal, uint8_t* out,
+                      int ds_h, int ds_w, const int32_t* ysrc_dev, const int32_t* xsrc_dev, void* stream) {
+    if (!slide || !label || !palette_dev || !out || !ysrc_dev || !xsrc_dev || slide_h <= 0 || slide_w <= 0 || ds_h <= 0 || ds_w <= 0 || n_pal <= 0 ||
+        n_pal > 256 || ds_h > 65535)
+        return ESPNET_EINVAL;
+    int gx = (ds_w + 255) / 256;
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, ds_h);
+    render_ds8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(slide, label, slide_w, palette_dev, n_pal, out, ds_h, ds_w, ysrc_dev, xsrc_dev);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+int espnet_class_counts(const uint8_t* maps, int B, size_t pix_per_map, int n_classes, unsigned long long* counts_dev, void* stream) {
+    if (!maps || !counts_dev || B <= 0 || B > 65535 || n_classes <= 0 || n_classes > 32) return ESPNET_EINVAL;
+    if (pix_per_map == 0) return ESPNET_OK;
+    size_t g = (pix_per_map + 256 * 64 - 1) / (256 * 64);
+    if (g > 148) g = 148;
+    if (g < 1) g = 1;
+    dim3 grid((unsigned)g, B);
+    class_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(maps, pix_per_map, n_classes, counts_dev);
     LAUNCH_COUNT();
     return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
 }

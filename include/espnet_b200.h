@@ -145,6 +145,32 @@ ESPNET_API int espnet_downsample_lut(const uint8_t* level0, int slide_h, int sli
 ESPNET_API int espnet_confusion_hist(const uint8_t* pred, const uint8_t* gt, size_t count, int n_classes,
                           unsigned long long* hist_dev, void* stream);
 
+/* ---------------- crop front-end and render ---------------- */
+
+/* Host LUTs reproducing OpenCV's index arithmetic bit-exactly: bilinear source index + weight of the +1 neighbour
+ * (cv2.resize INTER_LINEAR, generic code path) and nearest source index (INTER_NEAREST). */
+ESPNET_API int espnet_bilinear_lut(int src_len, int dst_len, int32_t* idx_host, float* weight_host);
+ESPNET_API int espnet_nearest_lut(int src_len, int dst_len, int32_t* idx_host);
+
+/* VisualizeResults_iou.py:107-119 for crops whose size differs from the network input: u8 BGR [B,h,w,3] -> fp32 NCHW [B,3,H,W]
+ * = cv2.resize(((float)p - mean) / std, (W, H)) / 255.  LUTs (device) from espnet_bilinear_lut(w, W) / (h, H). */
+ESPNET_API int espnet_preprocess_resize(const uint8_t* crops, int B, int h, int w, const float mean[3], const float std_[3],
+                                        const int32_t* xs_dev, const float* xf_dev, const int32_t* ys_dev, const float* yf_dev,
+                                        float* out, int H, int W, void* stream);
+/* VisualizeResults_iou.py:129: class maps [B,sh,sw] -> [B,dh,dw], cv2 INTER_NEAREST (LUTs from espnet_nearest_lut). */
+ESPNET_API int espnet_resize_nearest_u8(const uint8_t* src, int B, int sh, int sw, uint8_t* dst, int dh, int dw,
+                                        const int32_t* ysrc_dev, const int32_t* xsrc_dev, void* stream);
+/* VisualizeResults_iou.py:139-147: colour map (palette rows are r,g,b; written b,g,r) and cv2.addWeighted(img, .4, map, .6, 0).
+ * img / outputs are u8 [npix][3]; either output may be NULL. */
+ESPNET_API int espnet_palette_overlay(const uint8_t* img, const uint8_t* label, size_t npix, const uint8_t* palette_dev, int n_pal,
+                                      uint8_t* color_out, uint8_t* overlay_out, void* stream);
+/* eval_wsi_segmentation.py:225-240 (generate_whole_img over all windows): the /8 rendered slide u8 [ds_h][ds_w][3] from the
+ * level-0 slide [SH][SW][3] and the level-0 class map, LUTs as for espnet_downsample_lut. */
+ESPNET_API int espnet_render_ds8(const uint8_t* slide, const uint8_t* label, int slide_h, int slide_w, const uint8_t* palette_dev, int n_pal,
+                                 uint8_t* out, int ds_h, int ds_w, const int32_t* ysrc_dev, const int32_t* xsrc_dev, void* stream);
+/* VisualizeResults_iou.py:151-155: per-map class pixel counts, int64 [B][n_classes] on device (added to). */
+ESPNET_API int espnet_class_counts(const uint8_t* maps, int B, size_t pix_per_map, int n_classes, unsigned long long* counts_dev, void* stream);
+
 /* Hardware self-test of the tensor-core operand convention used by ESPNET_MODE_F16TC (no reference counterpart):
  * one 128 x nout x (8*nkc) tcgen05.mma whose A window is shifted by (dy, dx) pixels inside a TMA-staged (use_tma = 1)
  * or plainly copied (use_tma = 0) 48 x 48 activation box; *max_abs_err is measured against a host fp64 reference. */
