@@ -184,8 +184,15 @@ def kernel_roofline(name, per_launch_ms, B, hbm_peak, peak_src):
     if alg is None:
         return None
     ach = alg / (per_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")     # DRAM bytes per launch from the committed ncu --set full captures
+    if B == 64 and os.path.isfile(tp):
+        t = json.load(open(tp)).get(name)
+        if t:
+            traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
     roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg}
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": per_launch_ms,
+            "algorithmic_bytes_per_launch": alg}
     tf = flops / (per_launch_ms * 1e-3) / 1e12
     if "_tc3_" in name:
         roof["note"] = ("fp32-equivalent mode: the contraction runs on tcgen05 as 3 fp16 MMAs per product term set (3-term operand splits); "
