@@ -895,8 +895,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
             return run_branch_tc<2, 16, 16, 12>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
         }
         if (h->fp32_impl == 1) {   // fp32-equivalent on tensor cores: 3-term fp16 operand splits, fp32 accumulation
-            // (19 input channels fill 19/32 of the MMA K and the region loader dominates: the CUDA-core fp32 reduce is faster here)
-            r = down ? (h->tc_reduce == 2 ? run_reduce3x3_tc<19, 16, 2, true>(h, in, bw, o1h, B, H2, W2, st) : run_reduce3x3_f16<19, 12, 2, true>(h, in, bw.c1, o1h, B, H2, W2, st))
+            r = down ? (h->tc_reduce ? run_reduce3x3_tc<19, 16, 2, true>(h, in, bw, o1h, B, H2, W2, st) : run_reduce3x3_f16<19, 12, 2, true>(h, in, bw.c1, o1h, B, H2, W2, st))
                      : run_reduce1x1_tc<64, 16, 2, true>(h, in, bw, o1h, B, H4, W4, st);
             if (r) return r;
             return run_branch_tc<2, 16, 16, 12, true>(h, bw, o1h, down ? nullptr : in, out, out2, 131, c2_off, pk.b2_s, pk.b2_t, pk.b2_a, B, H4, W4, st);
