@@ -86,6 +86,7 @@ struct espnet_handle {
     Packed pk;
     std::map<std::string, StageRef> stages;
     int fp32_impl = 1;     // fp32 mode: 1 (default) = tensor cores with 3-term fp16 operand splits (fp32-equivalent), 0 = CUDA-core FMA kernels ("fp32_impl")
+    int l2_reverse = 1;    // 1x1 reduce walks its tiles against the order of the kernel that produced its input (L2 reuse)
     int tc_reduce = 1;     // f16tc mode: 1 = 1x1 reduce on tensor cores, 0 = CUDA-core fp32 reduce rounded to fp16 ("tc_reduce")
     int branch_impl = 0;   // 0 auto, 1 per-thread global loads, 2 TMA-staged (espnet_set_option "branch_impl")
     // per-kernel CUDA-event timing (espnet_set_profiling)
@@ -541,7 +542,9 @@ int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
     if (rc) return rc;
     const int grid = grid_for(h, (long long)B * ((HW + 127) / 128));
     { ProfScope _ps(h, SPLIT ? (CIN == 64 ? "reduce1x1_tc3_l2" : "reduce1x1_tc3_l3") : (CIN == 64 ? "reduce1x1_tc_l2" : "reduce1x1_tc_l3"), st);
-      reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kRedThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1)), o1h, B, HW); }
+      // the producer of `in` (a branch kernel) wrote its tiles in ascending order: walking them in DESCENDING order starts on
+      // the part that is still in the 126 MB L2 ("l2_reverse" option, default on)
+      reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kRedThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1)), o1h, B, HW, h->l2_reverse); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -753,6 +756,7 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (!h || !key) return ESPNET_EINVAL;
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "fp32_impl") == 0 && value >= 0 && value <= 1) { h->fp32_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "l2_reverse") == 0 && value >= 0 && value <= 1) { h->l2_reverse = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 2) { h->tc_reduce = value; return ESPNET_OK; }
     return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);
 }

@@ -64,7 +64,7 @@ __device__ __forceinline__ void store_o1_chunks(__half* __restrict__ o1h, int B,
 // w: [CIN/8][NOUT][8] fp16 (SPLIT: hi copy then lo copy), element (kc, n, j) = W1[co = n][ci = 8 kc + j] (zero for n >= CO)
 template <int CIN, int NOUT, int NKC, bool SPLIT>
 __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const float* __restrict__ in, const __half* __restrict__ w,
-                                                                      __half* __restrict__ o1h, int B, int HW) {
+                                                                      __half* __restrict__ o1h, int B, int HW, int reverse) {
     using Cfg = ReduceTcCfg<CIN, NOUT, SPLIT>;
     constexpr int KC = Cfg::KC;
     static_assert(CIN % 16 == 0 && NKC * 8 == NOUT, "shapes");
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
         const int lw = warp - 4, px = 32 * (lw & 3) + lane, kc0 = (lw >> 2) * (KC / 2);
         const uint32_t plane_b = (uint32_t)HW * 4u;
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int t_lin = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tile = reverse ? total_tiles - 1 - t_lin : t_lin;     // see the launcher: walk against the producer's order
             const int b = tile / chunks, p = (tile % chunks) * 128 + px;
             const bool ok = p < HW;
             const char* src = reinterpret_cast<const char*>(in + (size_t)b * CIN * HW + (ok ? p : 0));
@@ -175,7 +176,8 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
         // ===== epilogue: TMEM -> fp16 chunk-plane o1h =====
         const int q = warp & 3, px = 32 * q + lane;
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int t_lin = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tile = reverse ? total_tiles - 1 - t_lin : t_lin;
             const int b = tile / chunks, p = (tile % chunks) * 128 + px;
             const int s = it & 1;
             tc::mbar_wait(acc_full + s, (uint32_t)((it >> 1) & 1));
