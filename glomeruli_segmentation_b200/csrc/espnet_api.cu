@@ -20,6 +20,7 @@
 #include "kernels_tc_down.cuh"
 #include "kernels_wsi.cuh"
 #include "kernels_frontend.cuh"
+#include "kernels_dec.cuh"
 
 using namespace espnet;
 
@@ -86,6 +87,7 @@ struct espnet_handle {
     Packed pk;
     std::map<std::string, StageRef> stages;
     int fp32_impl = 1;     // fp32 mode: 1 (default) = tensor cores with 3-term fp16 operand splits (fp32-equivalent), 0 = CUDA-core FMA kernels ("fp32_impl")
+    int dec_impl = 1;      // decoder tail: 1 = 4 pixels per thread (dec_c4_kernel), 0 = 1 pixel per thread ("dec_impl")
     int l2_reverse = 1;    // 1x1 reduce walks its tiles against the order of the kernel that produced its input (L2 reuse)
     int tc_reduce = 1;     // f16tc mode: 1 = 1x1 reduce on tensor cores, 0 = CUDA-core fp32 reduce rounded to fp16 ("tc_reduce")
     int branch_impl = 0;   // 0 auto, 1 per-thread global loads, 2 TMA-staged (espnet_set_option "branch_impl")
@@ -631,7 +633,15 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         const size_t n = (size_t)B * H8 * W8;
         int grid = (int)((n + 255) / 256);
         if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
-        { ProfScope _ps(h, "head3", st); head3_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        const bool v4 = NC == 5 && h->dec_impl != 0 && (((size_t)H8 * W8) % 4 == 0) && ((uintptr_t)p.enc_out % 16 == 0);
+        if (v4) {
+            int g4 = (int)((n / 4 + 255) / 256);
+            if (g4 > 8 * h->num_sms) g4 = 8 * h->num_sms;
+            if (g4 < 1) g4 = 1;
+            { ProfScope _ps(h, "head3", st); head3v_kernel<NC><<<g4, 256, 0, st>>>(p); }
+        } else {
+            { ProfScope _ps(h, "head3", st); head3_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         if (!full) {
@@ -654,7 +664,14 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         const size_t n = (size_t)B * H4 * W4;
         int grid = (int)((n + 255) / 256);
         if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
-        { ProfScope _ps(h, "dec_a", st); dec_a_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        if (NC == 5 && h->dec_impl != 0 && (((size_t)H4 * W4) % 4 == 0)) {
+            int g4 = (int)((n / 4 + 255) / 256);
+            if (g4 > 8 * h->num_sms) g4 = 8 * h->num_sms;
+            if (g4 < 1) g4 = 1;
+            { ProfScope _ps(h, "dec_a", st); dec_av_kernel<NC><<<g4, 256, 0, st>>>(p); }
+        } else {
+            { ProfScope _ps(h, "dec_a", st); dec_a_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         h->stages["combine_l2_l3.0"] = {ws + L.t10, (size_t)B * 2 * NC * H4 * W4};
@@ -682,8 +699,15 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         p.logits = a->logits; p.mask = a->mask; p.prob_acc = a->prob_acc;
         p.prob_init = a->prob_init; p.mask_from_prob = a->mask_from_prob;
         p.B = B; p.H2 = H2; p.W2 = W2;
-        dim3 g((W2 + 31) / 32, (H2 + 7) / 8, B);
-        { ProfScope _ps(h, "dec_c", st); dec_c_kernel<NC><<<g, 256, 0, st>>>(p); }
+        // 4 pixels per thread (kernels_dec.cuh) when the vector stores are aligned; the one-pixel kernel otherwise / for 20 classes
+        const bool vec_ok = NC == 5 && (W2 % 4 == 0) && (((uintptr_t)p.logits | (uintptr_t)p.prob_acc) % 16 == 0) && ((uintptr_t)p.mask % 8 == 0);
+        if (vec_ok && h->dec_impl != 0) {
+            dim3 g((W2 / 4 + 31) / 32, (H2 + 7) / 8, B);
+            { ProfScope _ps(h, "dec_c", st); dec_c4_kernel<NC><<<g, 256, 0, st>>>(p); }
+        } else {
+            dim3 g((W2 + 31) / 32, (H2 + 7) / 8, B);
+            { ProfScope _ps(h, "dec_c", st); dec_c_kernel<NC><<<g, 256, 0, st>>>(p); }
+        }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
     }
@@ -756,6 +780,7 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (!h || !key) return ESPNET_EINVAL;
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "fp32_impl") == 0 && value >= 0 && value <= 1) { h->fp32_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "dec_impl") == 0 && value >= 0 && value <= 1) { h->dec_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "l2_reverse") == 0 && value >= 0 && value <= 1) { h->l2_reverse = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 2) { h->tc_reduce = value; return ESPNET_OK; }
     return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);
