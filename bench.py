@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -319,7 +319,6 @@ def run_ours(args):
     l0 = _lib.lib().espnet_launch_count()
     ms = timed(step_resident, args.steps)
     launches = int(_lib.lib().espnet_launch_count() - l0)
-    clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
     def join_pipe(start):
@@ -339,6 +338,7 @@ def run_ours(args):
         pipe.drain()
     ms_e2e = timed(step_e2e, args.steps, join_pipe)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (resident + end-to-end)
 
     # per-kernel share of the step (CUDA events on the launching stream, same inputs, separate pass)
     prof_steps = min(args.steps, 5)
