@@ -229,7 +229,8 @@ struct Packer {
         }
         if (!ok) return false;
         bw.chain = add(v);
-        {   // tensor-core copy [5 branches][9 taps][NKC][NOUT][8] fp16: element (n, ci) of tap t = W[co = n][ci][t], zero padded
+        {   // tensor-core copy [9 taps][NKC][5 branches][NOUT][8] fp16: element (n, ci) of tap t = W[co = n][ci][t], zero padded
+            // (the five branches are contiguous along N so that the centre tap of all of them is ONE wide MMA)
             const int nkc = 2 * ((n + 15) / 16), nout = n1 <= 16 ? 16 : 32;
             while (blob_h.size() % 64) blob_h.push_back(0);          // 128 B alignment (cp.async.bulk needs 16 B)
             bw.tc = blob_h.size() * sizeof(uint16_t);
@@ -246,7 +247,7 @@ struct Packer {
                             const __half hv = __float2half_rn(w->data[((size_t)o * n + c) * 9 + t]);
                             uint16_t bits;
                             std::memcpy(&bits, &hv, 2);
-                            dst[((((size_t)b * 9 + t) * nkc + c / 8) * nout + o) * 8 + (c % 8)] = bits;
+                            dst[((((size_t)t * nkc + c / 8) * 5 + b) * nout + o) * 8 + (c % 8)] = bits;
                         }
             }
         }
@@ -306,9 +307,16 @@ struct Packer {
                         for (int c = 0; c < n; ++c) {
                             uint16_t hi, lo;
                             split(w->data[((size_t)o * n + c) * 9 + t], hi, lo);
-                            const size_t idx = (size_t)(c / 16) * unit + ((((size_t)b * 9 + t) * 2 + (c % 16) / 8) * nout + o) * 8 + (c % 8);
-                            dst[idx] = hi;
-                            dst[(size_t)ks_n * unit + idx] = lo;
+                            if (ks_n == 1) {
+                                // one K step: merged unit [tap][2][branch][hi NOUT | lo NOUT][8] -- A_hi x [W_hi | W_lo] is one N = 2 NOUT MMA
+                                const size_t idx = ((((size_t)t * 2 + c / 8) * 5 + b) * 2 * nout + o) * 8 + (c % 8);
+                                dst[idx] = hi;
+                                dst[idx + (size_t)nout * 8] = lo;
+                            } else {
+                                const size_t idx = (size_t)(c / 16) * unit + ((((size_t)t * 2 + (c % 16) / 8) * 5 + b) * nout + o) * 8 + (c % 8);
+                                dst[idx] = hi;
+                                dst[(size_t)ks_n * unit + idx] = lo;
+                            }
                         }
             }
             if (down) {    // 3x3 stride-2 reduce: [hi|lo][ks][tap][2][NOUT][8]
@@ -896,7 +904,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
         p.l1_s = P + pk.l1_s; p.l1_t = P + pk.l1_t; p.l1_a = P + pk.l1_a;
         p.b1_s = P + pk.b1_s; p.b1_t = P + pk.b1_t; p.b1_a = P + pk.b1_a;
         p.out0cat = ws + L.out0cat; p.inp1raw = ws + L.inp1raw;
-        dim3 grid((W2 + 31) / 32, (H2 + 7) / 8, B);
+        dim3 grid((W2 + kStemTW - 1) / kStemTW, (H2 + kStemTH - 1) / kStemTH, B);
         {
             ProfScope _ps(h, "stem", st);
             if (a->in_fmt == 0) stem_kernel<0><<<grid, 256, 0, st>>>(p);

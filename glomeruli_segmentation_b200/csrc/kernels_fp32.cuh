@@ -91,87 +91,183 @@ struct StemParams {
     float* inp1raw;
 };
 
+// Block = 32 x 16 outputs (thread: column lane, rows ty and ty + 8).  The 65 x 33 input region is staged ONCE in shared
+// memory, already normalised (u8 inputs go through a 3 x 256 table built with the reference's three separate fp32
+// roundings, so the 54 divisions per output of a direct evaluation disappear), split by column parity so that the
+// stride-2 window reads of a warp are bank-conflict free.  Accumulation order (channel, then tap) is fixed.
+constexpr int kStemTW = 32, kStemTH = 16;
+constexpr int kStemRW = 2 * kStemTW + 1, kStemRH = 2 * kStemTH + 1;      // 65 x 33 input region
+constexpr int kStemPE = 33, kStemPO = 32;                               // even / odd column counts
+
 template <int FMT>
-__global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
+__global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
     __shared__ __align__(16) float sw[27 * 16];
     __shared__ float sp[3 * 16 + 3 * 19];
-    for (int i = threadIdx.x; i < 27 * 16; i += 256) sw[i] = p.w1[i];
-    for (int i = threadIdx.x; i < 16; i += 256) { sp[i] = p.l1_s[i]; sp[16 + i] = p.l1_t[i]; sp[32 + i] = p.l1_a[i]; }
-    for (int i = threadIdx.x; i < 19; i += 256) { sp[48 + i] = p.b1_s[i]; sp[67 + i] = p.b1_t[i]; sp[86 + i] = p.b1_a[i]; }
+    __shared__ float lut[FMT == 0 ? 1 : 3 * 256];
+    __shared__ float se[3][kStemRH][kStemPE];      // region columns 0, 2, 4, ..
+    __shared__ float so[3][kStemRH][kStemPO];      // region columns 1, 3, 5, ..
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 27 * 16; i += 256) sw[i] = p.w1[i];
+    for (int i = tid; i < 16; i += 256) { sp[i] = p.l1_s[i]; sp[16 + i] = p.l1_t[i]; sp[32 + i] = p.l1_a[i]; }
+    for (int i = tid; i < 19; i += 256) { sp[48 + i] = p.b1_s[i]; sp[67 + i] = p.b1_t[i]; sp[86 + i] = p.b1_a[i]; }
+    if (FMT != 0) {
+        // three separate fp32 roundings, exactly as numpy does them (VisualizeResults_iou.py:107-119)
+        for (int i = tid; i < 3 * 256; i += 256) {
+            const int c = i >> 8;
+            lut[i] = __fdiv_rn(__fdiv_rn(__fsub_rn((float)(i & 255), p.mean[c]), p.stdv[c]), 255.f);
+        }
+    }
     __syncthreads();
     const int H2 = p.H >> 1, W2 = p.W >> 1;
-    const int x2 = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y2 = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int b = blockIdx.z;
-    if (x2 >= W2 || y2 >= H2) return;
+    const int ry0 = 2 * (int)blockIdx.y * kStemTH - 1, rx0 = 2 * (int)blockIdx.x * kStemTW - 1;   // region origin in the crop
 
-    long long ox = 0, oy = 0;
-    if (FMT == 2) { ox = p.origins[2 * b]; oy = p.origins[2 * b + 1]; }
-    float v[3][9];
+    auto put = [&](int c, int r, int j, float v) {
+        if (j & 1) so[c][r][j >> 1] = v; else se[c][r][j >> 1] = v;
+    };
+    if (FMT == 0) {
+        const float* x = reinterpret_cast<const float*>(p.x);
+        for (int row = tid >> 5; row < 3 * kStemRH; row += 8) {      // one warp per (channel, region row)
+            const int c = row / kStemRH, r = row - c * kStemRH;
+            const int yy = ry0 + r;
+            const bool row_ok = yy >= 0 && yy < p.H;
+            const float* xr = x + ((size_t)(b * 3 + c) * p.H + (row_ok ? yy : 0)) * p.W;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+            for (int k = 0; k < 3; ++k) {
+                const int j = (tid & 31) + 32 * k;
+                if (j >= kStemRW) continue;
+                const int xx = rx0 + j;
+                // asynchronous 4-byte copies (all of a warp's rows in flight at once); src-size 0 = zero fill =
+                // conv / pool zero padding of the NORMALISED tensor (Model.py:20,230)
+                const bool ok = row_ok && xx >= 0 && xx < p.W;
+                float* dst = (j & 1) ? &so[c][r][j >> 1] : &se[c][r][j >> 1];
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                             "l"(ok ? xr + xx : x), "r"(ok ? 4 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+        // u8 HWC rows: 195 contiguous bytes per region row, fetched as aligned 32-bit words
+        const unsigned char* x = reinterpret_cast<const unsigned char*>(p.x);
+        long long ox = 0, oy = 0, pitch_px = p.W, rows = p.H, row0 = (long long)b * p.H;
+        if (FMT == 2) { ox = p.origins[2 * b]; oy = p.origins[2 * b + 1]; pitch_px = p.slide_w; rows = p.slide_h; row0 = 0; }
+        const size_t total = FMT == 2 ? (size_t)p.slide_h * p.slide_w * 3 : (size_t)p.B * p.H * p.W * 3;
+        constexpr int kWordsPerRow = (kStemRW * 3 + 3 + 3) / 4;     // 195 bytes + up to 3 bytes of misalignment
+        constexpr int kRowsPerWarp = (kStemRH + 7) / 8, kWordsPerLane = (kWordsPerRow + 31) / 32;
+        // phase 1: every word this thread is responsible for (one warp per region row), all loads in flight at once
+        unsigned int words[kRowsPerWarp][kWordsPerLane];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int yy = 2 * y2 - 1 + ky, xx = 2 * x2 - 1 + kx;
-            const bool in = (yy >= 0) && (yy < p.H) && (xx >= 0) && (xx < p.W);
+        for (int ri = 0; ri < kRowsPerWarp; ++ri) {
+            const int r = (tid >> 5) + 8 * ri;
+            const int yy = ry0 + r;
+            const long long sy = oy + yy;                            // row in the source image
+            const bool row_ok = r < kStemRH && yy >= 0 && yy < p.H && sy >= 0 && sy < rows;
+            // byte address of region column 0 in this row (may be negative / outside: only used for alignment and bounds)
+            const long long a0 = ((row0 + sy) * pitch_px + (ox + rx0)) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float val = 0.f;   // conv / pool zero padding of the NORMALISED tensor (Model.py:20,230)
-                if (in) {
-                    if (FMT == 0) {
-                        val = __ldg(reinterpret_cast<const float*>(p.x) + ((size_t)(b * 3 + c) * p.H + yy) * p.W + xx);
-                    } else {
-                        unsigned int u = 0;   // outside the slide openslide pads with 0
-                        if (FMT == 1) {
-                            u = __ldg(reinterpret_cast<const unsigned char*>(p.x) + ((size_t)((size_t)b * p.H + yy) * p.W + xx) * 3 + c);
-                        } else {
-                            const long long sx = ox + xx, sy = oy + yy;
-                            if (sx >= 0 && sy >= 0 && sx < p.slide_w && sy < p.slide_h)
-                                u = __ldg(reinterpret_cast<const unsigned char*>(p.x) + ((size_t)sy * p.slide_w + sx) * 3 + c);
-                        }
-                        // three separate fp32 roundings, exactly as numpy does them
-                        val = __fdiv_rn(__fdiv_rn(__fsub_rn((float)u, p.mean[c]), p.stdv[c]), 255.f);
-                    }
+            for (int k = 0; k < kWordsPerLane; ++k) {
+                const int wi = (tid & 31) + 32 * k;
+                const long long aw = ((a0 >> 2) + wi) << 2;          // aligned word address (arithmetic shift floors)
+                unsigned int word = 0;
+                if (row_ok && wi < kWordsPerRow && aw >= 0 && (size_t)aw < total) {
+                    if ((size_t)aw + 4 <= total) word = __ldg(reinterpret_cast<const unsigned int*>(x + aw));
+                    else for (int q = 0; q < 4 && (size_t)aw + q < total; ++q) word |= (unsigned int)x[aw + q] << (8 * q);
                 }
-                v[c][ky * 3 + kx] = val;
+                words[ri][k] = word;
+            }
+        }
+        // phase 2: bytes -> (pixel, channel) -> table -> shared memory
+#pragma unroll
+        for (int ri = 0; ri < kRowsPerWarp; ++ri) {
+            const int r = (tid >> 5) + 8 * ri;
+            if (r >= kStemRH) continue;
+            const int yy = ry0 + r;
+            const long long sy = oy + yy;
+            const bool row_in_crop = yy >= 0 && yy < p.H;
+            const bool row_in_src = sy >= 0 && sy < rows;
+            const long long a0 = ((row0 + sy) * pitch_px + (ox + rx0)) * 3;
+            const int lead = (int)(a0 - ((a0 >> 2) << 2));           // bytes of the first word before region column 0
+#pragma unroll
+            for (int k = 0; k < kWordsPerLane; ++k) {
+                const int wi = (tid & 31) + 32 * k;
+                if (wi >= kWordsPerRow) continue;
+                const unsigned int word = words[ri][k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int off = 4 * wi - lead + q;               // byte offset inside the region row
+                    if (off < 0 || off >= kStemRW * 3) continue;
+                    const int j = (off * 171) >> 9, c = off - 3 * j; // off / 3 for off < 256
+                    const int xx = rx0 + j;
+                    const long long sx = ox + xx;
+                    float v = 0.f;                                   // zero padding of the normalised tensor
+                    if (row_in_crop && xx >= 0 && xx < p.W) {
+                        // outside the slide openslide pads with 0 (then normalised like any pixel)
+                        const unsigned int u = (row_in_src && sx >= 0 && sx < pitch_px) ? ((word >> (8 * q)) & 255u) : 0u;
+                        v = lut[c * 256 + u];
+                    }
+                    put(c, r, j, v);
+                }
             }
         }
     }
-    const size_t plane = (size_t)H2 * W2;
-    const size_t pix = (size_t)y2 * W2 + x2;
-    float acc[16];
+    __syncthreads();
+
+    const int lane = tid & 31, ty = tid >> 5;
+    const int x2 = blockIdx.x * kStemTW + lane;
+    const int y2a = blockIdx.y * kStemTH + ty;
+    float acc[2][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+        for (int j = 0; j < 16; ++j) acc[r][j] = 0.f;
+    float pool[2][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const float a = v[c][t];
+            const int ky = t / 3, kx = t % 3;
+            // region column 2 lane + kx: kx = 0, 2 even (index lane, lane + 1), kx = 1 odd (index lane)
+            const float a0 = kx == 1 ? so[c][2 * ty + ky][lane] : se[c][2 * ty + ky][lane + (kx >> 1)];
+            const float a1 = kx == 1 ? so[c][2 * (ty + 8) + ky][lane] : se[c][2 * (ty + 8) + ky][lane + (kx >> 1)];
+            s0 += a0; s1 += a1;
             const float4* w4 = reinterpret_cast<const float4*>(sw + (c * 9 + t) * 16);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 w = w4[j4];
-                acc[4 * j4 + 0] = fmaf(a, w.x, acc[4 * j4 + 0]);
-                acc[4 * j4 + 1] = fmaf(a, w.y, acc[4 * j4 + 1]);
-                acc[4 * j4 + 2] = fmaf(a, w.z, acc[4 * j4 + 2]);
-                acc[4 * j4 + 3] = fmaf(a, w.w, acc[4 * j4 + 3]);
+                acc[0][4 * j4 + 0] = fmaf(a0, w.x, acc[0][4 * j4 + 0]);
+                acc[0][4 * j4 + 1] = fmaf(a0, w.y, acc[0][4 * j4 + 1]);
+                acc[0][4 * j4 + 2] = fmaf(a0, w.z, acc[0][4 * j4 + 2]);
+                acc[0][4 * j4 + 3] = fmaf(a0, w.w, acc[0][4 * j4 + 3]);
+                acc[1][4 * j4 + 0] = fmaf(a1, w.x, acc[1][4 * j4 + 0]);
+                acc[1][4 * j4 + 1] = fmaf(a1, w.y, acc[1][4 * j4 + 1]);
+                acc[1][4 * j4 + 2] = fmaf(a1, w.z, acc[1][4 * j4 + 2]);
+                acc[1][4 * j4 + 3] = fmaf(a1, w.w, acc[1][4 * j4 + 3]);
             }
         }
-    float* o = p.out0cat + (size_t)b * 19 * plane + pix;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        float y = bn_prelu(acc[j], sp[j], sp[16 + j], sp[32 + j]);       // level1.bn + level1.act
-        y = bn_prelu(y, sp[48 + j], sp[67 + j], sp[86 + j]);              // b1 on channels 0..15
-        o[(size_t)j * plane] = y;
+        pool[0][c] = s0 / 9.f;                                            // count_include_pad: always / 9
+        pool[1][c] = s1 / 9.f;
     }
+    if (x2 >= W2) return;
+    const size_t plane = (size_t)H2 * W2;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float s = 0.f;
+    for (int r = 0; r < 2; ++r) {
+        const int y2 = y2a + 8 * r;
+        if (y2 >= H2) continue;
+        const size_t pix = (size_t)y2 * W2 + x2;
+        float* o = p.out0cat + (size_t)b * 19 * plane + pix;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) s += v[c][t];
-        s = s / 9.f;                                                      // count_include_pad: always / 9
-        p.inp1raw[(size_t)(b * 3 + c) * plane + pix] = s;
-        o[(size_t)(16 + c) * plane] = bn_prelu(s, sp[48 + 16 + c], sp[67 + 16 + c], sp[86 + 16 + c]);
+        for (int j = 0; j < 16; ++j) {
+            float y = bn_prelu(acc[r][j], sp[j], sp[16 + j], sp[32 + j]);    // level1.bn + level1.act
+            y = bn_prelu(y, sp[48 + j], sp[67 + j], sp[86 + j]);              // b1 on channels 0..15
+            o[(size_t)j * plane] = y;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float s = pool[r][c];
+            p.inp1raw[(size_t)(b * 3 + c) * plane + pix] = s;
+            o[(size_t)(16 + c) * plane] = bn_prelu(s, sp[48 + 16 + c], sp[67 + 16 + c], sp[86 + 16 + c]);
+        }
     }
 }
 

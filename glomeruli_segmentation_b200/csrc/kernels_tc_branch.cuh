@@ -12,11 +12,15 @@
 //     32-bit words so that box rows are 640 B contiguous runs.  The zero padding of every conv is TMA's out-of-bounds
 //     fill.  Tap (ky,kx) of dilation d is the SAME buffer read through a UMMA descriptor whose start address is moved
 //     by ((ky-1)*d*40 + (kx-1)*d) * 16 B: the implicit-GEMM window shift costs no data movement.
-//   * B operand: all five branches' weights [br][tap][kc][NOUT][8] fp16, resident in shared memory for the whole
-//     persistent CTA (one cp.async.bulk at kernel start; 90 KB at level 3, 22.5 KB at level 2).
+//   * B operand: all five branches' weights [tap][kc][br][NOUT][8] fp16, resident in shared memory for the whole
+//     persistent CTA (one cp.async.bulk at kernel start; 90 KB at level 3, 22.5 KB at level 2).  The branches are
+//     contiguous along N: the centre tap reads the SAME A window for every dilation, so it is ONE MMA of N = 5 NOUT
+//     into the five adjacent accumulators instead of five (small-N MMAs cost a fixed ~57 cycles each on this part).
+//   * Taps whose whole 8x16 window lies in the zero padding (d = 8, 16 near the map border) CAN be predicated off
+//     (ESPNET_TC_NOSKIP=0); measured slower than issuing them, see the macro.
 //   * D: five accumulators of NOUT fp32 columns per tile, THREE tiles deep in TMEM, so that the epilogue of tile i
 //     runs while TMA and the tensor core work on tiles i+1 and i+2.
-//   * MMA order per tile: K step outer, (branch, tap) inner -- stage s only needs the K chunks of step s, so the TMA
+//   * MMA order per tile: K step outer, centre tap then (branch, tap) inner -- stage s only needs the K chunks of step s, so the TMA
 //     of the next tile's first half overlaps the second half's MMAs.
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane of the converged warp), warp 2 = TMEM allocator,
 //     warp 3 = L2 prefetcher of the residual, warps 4..19 = epilogue: TMEM -> registers, HFF sums, residual + BN +
@@ -39,10 +43,19 @@ constexpr int kTcAccStages = 3;
 #ifndef ESPNET_TC_PREFETCH_LEAD
 #define ESPNET_TC_PREFETCH_LEAD 3
 #endif
-constexpr int kTcPrefetchLead = ESPNET_TC_PREFETCH_LEAD;   // tiles the L2 prefetcher runs ahead of the epilogue
+constexpr int kTcPrefetchLead = ESPNET_TC_PREFETCH_LEAD;
+#ifndef ESPNET_TC_NOSKIP
+// 0: predicate off the taps whose window lies entirely in the zero padding (8 % of the level-3 MMAs).  Measured SLOWER
+// (0.976 -> 1.006 ms per 9 level-3 launches): a predicated-off UTCHMMA still costs the issuing thread its descriptor
+// arithmetic and the predicate tests lengthen the single-thread issue loop, so the default issues every tap.
+#define ESPNET_TC_NOSKIP 1
+#endif
+#ifndef ESPNET_TC_NOWSTREAM
+#define ESPNET_TC_NOWSTREAM 0   // 1: TIMING EXPERIMENT ONLY (wrong results): load the streamed split weights once
+#endif   // tiles the L2 prefetcher runs ahead of the epilogue
 
 struct BranchTcParams {
-    const __half* w;        // [5][9][NKC][NOUT][8] fp16 (d1, d2, d4, d8, d16)
+    const __half* w;        // [9][NKC][5][NOUT][8] fp16 (d1, d2, d4, d8, d16); split variants: see BranchTcCfg
     const float* res;       // [B,C,H,W] residual input or nullptr
     const float *s, *t, *a; // BN scale/shift + PReLU slope (C)
     float* out;             // [B,C,H,W] or nullptr
@@ -56,10 +69,12 @@ template <int NKC, int NOUT, bool SPLIT = false>
 struct BranchTcCfg {
     static constexpr int KS = NKC / 2;                            // K = 16 steps per tile
     static constexpr int W_BRANCH = 9 * NKC * NOUT * 16;          // bytes of one branch's weights (plain layout)
-    static constexpr int W_UNIT = 5 * 9 * 2 * NOUT * 16;          // split layout: all branches, one K step, hi OR lo
+    static constexpr int W_UNIT = 5 * 9 * 2 * NOUT * 16;          // split layout [tap][2][br][NOUT][8]: one K step, hi OR lo
     static constexpr bool W_STREAM = SPLIT && KS > 1;             // split weights do not fit: 2-unit ring, else resident
+    static constexpr bool MERGE = SPLIT && KS == 1;               // one K step: [tap][2][br][hi NOUT | lo NOUT][8], resident
+    static constexpr int NB = MERGE ? 2 * NOUT : NOUT;            // weight rows = accumulator columns per branch
     static constexpr int W_BYTES = SPLIT ? 2 * W_UNIT : 5 * W_BRANCH;
-    static constexpr int ACC_COLS = 5 * NOUT;                     // TMEM columns per tile
+    static constexpr int ACC_COLS = 5 * NB;                       // TMEM columns per tile
     static constexpr int TMEM_COLS = (kTcAccStages * ACC_COLS <= 256) ? 256 : 512;
     static constexpr int EP_BYTES = 2 * 128 * 16;                 // two float4 tables of 128 channels
     static constexpr size_t SMEM = 1024 + 2 * (size_t)kTcStage + (size_t)W_BYTES + EP_BYTES + 256;
@@ -76,6 +91,9 @@ struct BranchTcCfg {
 // 0 and the lo half-box to stage 1, and the weights [hi|lo][K step][branch][tap][2][NOUT][8] stream through a 2-unit
 // ring (unit 0 = W_hi(k), unit 1 = W_lo(k)) because hi + lo of all branches (180 KB) do not fit next to the boxes.
 // MMA order per K step: A_lo x W_hi, A_hi x W_hi, A_hi x W_lo -- 3x the MMAs of the plain variant.
+// With a single K step (level 2, Cfg::MERGE) TMEM has room for separate hi / lo accumulators: the weights are resident
+// as [W_hi | W_lo] rows, A_hi x [W_hi | W_lo] is ONE N = 2 NOUT MMA, A_lo x W_hi a second one, and the epilogue adds the
+// two accumulator halves -- 2x the MMAs of the plain variant.
 template <int NKC, int NOUT, int CO1, int CO, int VAR, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BranchTcParams p) {
     using Cfg = BranchTcCfg<NKC, NOUT, SPLIT>;
@@ -144,6 +162,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                         tc::tma_load_4d(abuf + s * kTcStage, &tmap, a_full + s, 4 * (tx * kTcTileW - kTcHalo2), ty * kTcTileH - kTcHalo2, 2 * ks, b);
                     }
                 }
+            } else if constexpr (Cfg::MERGE) {
+                // merged weights once; per tile A_hi -> stage 0, then A_lo -> stage 1 (the order the MMA issuer needs them)
+                tc::mbar_expect_tx(w_full, Cfg::W_BYTES);
+                tc::bulk_g2s(wbuf, p.w, Cfg::W_BYTES, w_full);
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+                    const int cx = 4 * (tx * kTcTileW - kTcHalo2), cy = ty * kTcTileH - kTcHalo2;
+                    const uint32_t par = (uint32_t)(it & 1);
+                    tc::mbar_wait(a_empty + 0, par ^ 1);
+                    tc::mbar_expect_tx(a_full + 0, kTcStage);
+                    tc::tma_load_4d(abuf, &tmap, a_full + 0, cx, cy, 0, b);
+                    tc::mbar_wait(a_empty + 1, par ^ 1);
+                    tc::mbar_expect_tx(a_full + 1, kTcStage);
+                    tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 0, b + p.B);
+                }
             } else {
                 // per K step n: W_hi(k) -> unit 0, A_lo(k) -> stage 1, A_hi(k) -> stage 0, W_lo(k) -> unit 1 (the order in
                 // which the MMA issuer frees / needs them)
@@ -159,16 +193,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                         tc::mbar_wait(a_empty + 1, par ^ 1);
                         tc::mbar_expect_tx(a_full + 1, kTcStage);
                         tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 2 * ks, b + p.B);
-                        if (Cfg::W_STREAM || n == 0) {
-                            if (Cfg::W_STREAM) tc::mbar_wait(w_empty + 0, par ^ 1);
+                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) {
+                            if (!ESPNET_TC_NOWSTREAM) tc::mbar_wait(w_empty + 0, par ^ 1);
                             tc::mbar_expect_tx(w_full + 0, Cfg::W_UNIT);
                             tc::bulk_g2s(wbuf, wg + (size_t)ks * Cfg::W_UNIT, Cfg::W_UNIT, w_full + 0);
                         }
                         tc::mbar_wait(a_empty + 0, par ^ 1);
                         tc::mbar_expect_tx(a_full + 0, kTcStage);
                         tc::tma_load_4d(abuf, &tmap, a_full + 0, cx, cy, 2 * ks, b);
-                        if (Cfg::W_STREAM || n == 0) {
-                            if (Cfg::W_STREAM) tc::mbar_wait(w_empty + 1, par ^ 1);
+                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) {
+                            if (!ESPNET_TC_NOWSTREAM) tc::mbar_wait(w_empty + 1, par ^ 1);
                             tc::mbar_expect_tx(w_full + 1, Cfg::W_UNIT);
                             tc::bulk_g2s(wbuf + Cfg::W_UNIT, wg + (size_t)(KS + ks) * Cfg::W_UNIT, Cfg::W_UNIT, w_full + 1);
                         }
@@ -179,32 +213,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the control flow converged, one elected lane issues =====
         {
-            constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
+            constexpr int NB = Cfg::NB;
             // Descriptors as (hi, lo) words: hi = SBO | version is constant per operand, lo = start>>4 | LBO<<12 and
             // every window shift / tap is an ADD on lo in 16 B units.  One thread issues everything, so the per-MMA
             // instruction count IS the issue rate: taps are unrolled with constant offsets.
             constexpr uint32_t a_hi = (uint32_t)((kTcBoxW * 16) >> 4) | (1u << 14);
             constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
             const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + (uint32_t)(kTcHalo2 * kTcBoxW + kTcHalo2) + ((uint32_t)(kTcPlane2 >> 4) << 16);
-            const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
-            // 45 MMAs: all branches and taps of one K step; a_lo_s = A stage, b_lo_s = weights of branch 0 / tap 0,
-            // b_br / b_tap = weight strides in 16 B units, fresh = first K step of the tile (overwrite the accumulators);
-            // afterwards up to three mbarriers receive the completion of everything issued so far (tcgen05.commit).
-            auto issue45 = [&](uint32_t a_lo_s, uint32_t b_lo_s, uint32_t b_br, uint32_t b_tap, uint32_t d_tile, bool fresh,
-                               uint64_t* c0, uint64_t* c1, uint64_t* c2) {
+            const uint32_t b_lo0 = (tc::smem_addr(wbuf) >> 4) + ((uint32_t)((5 * NB * 16) >> 4) << 16);   // K chunk stride = 5 NB rows
+            // All MMAs of one (K step, operand pair): the centre tap of the five branches as one N = 5 NB MMA (CENTER) or
+            // five N = NBR ones, then the 8 outer taps per branch, N = NBR columns at accumulator column br * NB.
+            // a_lo_s = A stage, b_lo_s = weights of tap 0 / branch 0 of this K step, b_tap = tap stride (16 B units),
+            // fresh = first MMAs of the tile (the centre tap overwrites the accumulators), vm = tap validity bits of
+            // this tile (4 per branch: top, bottom, left, right window not entirely in the padding).  Afterwards up to
+            // three mbarriers receive the completion of everything issued so far (tcgen05.commit).
+            auto issue_step = [&](auto nbr_tag, auto center_tag, uint32_t a_lo_s, uint32_t b_lo_s, uint32_t b_tap, uint32_t d_tile,
+                                  bool fresh, uint32_t vm, uint64_t* c0, uint64_t* c1, uint64_t* c2) {
+                constexpr int NBR = decltype(nbr_tag)::value;
+                constexpr bool CENTER = decltype(center_tag)::value != 0;
+                constexpr uint32_t idesc = tc::umma_idesc_f16(NBR);
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
+                    const uint64_t adesc_c = ((uint64_t)a_hi << 32) | (uint64_t)a_lo_s;
+                    if constexpr (CENTER) {
+                        constexpr uint32_t idesc_c = tc::umma_idesc_f16(5 * NB);
+                        tc::umma_f16(d_tile, adesc_c, ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_s + 4u * b_tap), idesc_c, fresh ? 0u : 1u);
+                    }
 #pragma unroll 1
                     for (int br = 0; br < 5; ++br) {
                         const int d = 1 << br, dp = d * kTcBoxW;
-                        const uint32_t b_lo = b_lo_s + (uint32_t)br * b_br;
-                        const uint32_t d_tmem = d_tile + (uint32_t)(br * NOUT);
+                        const uint32_t b_lo = b_lo_s + (uint32_t)(br * NB);
+                        const uint32_t d_tmem = d_tile + (uint32_t)(br * NB);
+                        const uint32_t m = vm >> (4 * br);
+                        if constexpr (!CENTER)
+                            tc::umma_f16(d_tmem, adesc_c, ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 4u * b_tap), idesc, fresh ? 0u : 1u);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
+                            if (tap == 4) continue;
                             const int ky = tap / 3 - 1, kx = tap % 3 - 1;           // compile-time after unrolling
+                            const uint32_t need = (ky < 0 ? 1u : ky > 0 ? 2u : 0u) | (kx < 0 ? 4u : kx > 0 ? 8u : 0u);
                             const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + (uint32_t)(ky * dp + kx * d));
                             const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)tap * b_tap);
-                            tc::umma_f16(d_tmem, adesc, bdesc, idesc, (fresh && tap == 0) ? 0u : 1u);
+                            // predicated off when the window lies entirely in the zero padding
+                            tc::umma_f16_acc_if((m & need) == need ? 1u : 0u, d_tmem, adesc, bdesc, idesc);
                         }
                     }
                     if (c0) tc::umma_commit(c0);
@@ -213,11 +264,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                 }
                 __syncwarp();
             };
+            // tap validity of a tile: bit 4 br + {0: ky = 0, 1: ky = 2, 2: kx = 0, 3: kx = 2}
+            auto tap_mask = [&](int it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int x0 = (tile % tiles_x) * kTcTileW, y0 = ((tile / tiles_x) % tiles_y) * kTcTileH;
+                uint32_t vm = 0;
+#pragma unroll
+                for (int br = 0; br < 5; ++br) {
+                    const int d = 1 << br;
+                    vm |= (uint32_t)(y0 - d + kTcTileH - 1 >= 0) << (4 * br);
+                    vm |= (uint32_t)(y0 + d < H) << (4 * br + 1);
+                    vm |= (uint32_t)(x0 - d + kTcTileW - 1 >= 0) << (4 * br + 2);
+                    vm |= (uint32_t)(x0 + d < W) << (4 * br + 3);
+                }
+#if ESPNET_TC_NOSKIP
+                vm = 0xFFFFFu;
+#endif
+                return vm;
+            };
             if constexpr (!SPLIT) {
                 tc::mbar_wait(w_full, 0);
                 int c = 0;
                 for (int it = 0; it < my_tiles; ++it) {
                     const int as = it % kTcAccStages;
+                    const uint32_t vm = tap_mask(it);
                     tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
                     const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
 #pragma unroll
@@ -226,36 +296,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                         tc::mbar_wait(a_full + s, (uint32_t)((c >> 1) & 1));
                         __syncwarp();
                         // the half-box is reusable once these MMAs have read it; after the last K step the tile is complete
-                        issue45(a_lo0 + (uint32_t)(s * (kTcStage >> 4)), b_lo0 + (uint32_t)(2 * ks * NOUT), (uint32_t)(Cfg::W_BRANCH >> 4),
-                                (uint32_t)(NKC * NOUT), d_tile, ks == 0, a_empty + s, ks == KS - 1 ? acc_full + as : nullptr, nullptr);
+                        issue_step(IntTag<NOUT>(), IntTag<1>(), a_lo0 + (uint32_t)(s * (kTcStage >> 4)), b_lo0 + (uint32_t)(2 * ks * 5 * NOUT),
+                                   (uint32_t)(NKC * 5 * NOUT), d_tile, ks == 0, vm, a_empty + s, ks == KS - 1 ? acc_full + as : nullptr, nullptr);
                     }
                 }
+            } else if constexpr (Cfg::MERGE) {
+                constexpr uint32_t TAP = 2 * 5 * NB;
+                tc::mbar_wait(w_full, 0);
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int as = it % kTcAccStages;
+                    const uint32_t par = (uint32_t)(it & 1);
+                    const uint32_t vm = tap_mask(it);
+                    tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
+                    const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
+                    // (1) A_hi x [W_hi | W_lo]: N = 2 NOUT per branch, both accumulator halves
+                    tc::mbar_wait(a_full + 0, par);
+                    __syncwarp();
+                    issue_step(IntTag<NB>(), IntTag<1>(), a_lo0, b_lo0, TAP, d_tile, true, vm, a_empty + 0, nullptr, nullptr);
+                    // (2) A_lo x W_hi: N = NOUT per branch into the hi halves
+                    tc::mbar_wait(a_full + 1, par);
+                    __syncwarp();
+                    issue_step(IntTag<NOUT>(), IntTag<0>(), a_lo0 + (uint32_t)(kTcStage >> 4), b_lo0, TAP, d_tile, false, vm, a_empty + 1,
+                               acc_full + as, nullptr);
+                }
             } else {
-                constexpr uint32_t BR = 9 * 2 * NOUT, TAP = 2 * NOUT;       // split weight layout strides (16 B units)
+                constexpr uint32_t TAP = 2 * 5 * NOUT;                       // split weight layout: tap stride (16 B units)
                 const uint32_t a_st0 = a_lo0, a_st1 = a_lo0 + (uint32_t)(kTcStage >> 4);
                 const uint32_t w_u0 = b_lo0, w_u1 = b_lo0 + (uint32_t)(Cfg::W_UNIT >> 4);
                 int n = 0;
                 for (int it = 0; it < my_tiles; ++it) {
                     const int as = it % kTcAccStages;
+                    const uint32_t vm = tap_mask(it);
                     tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
                     const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks, ++n) {
                         const uint32_t par = (uint32_t)(n & 1);
                         // (1) A_lo x W_hi
-                        if (Cfg::W_STREAM || n == 0) tc::mbar_wait(w_full + 0, Cfg::W_STREAM ? par : 0u);
+                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) tc::mbar_wait(w_full + 0, par);
                         tc::mbar_wait(a_full + 1, par);
                         __syncwarp();
-                        issue45(a_st1, w_u0, BR, TAP, d_tile, ks == 0, a_empty + 1, nullptr, nullptr);
+                        issue_step(IntTag<NOUT>(), IntTag<1>(), a_st1, w_u0, TAP, d_tile, ks == 0, vm, a_empty + 1, nullptr, nullptr);
                         // (2) A_hi x W_hi
                         tc::mbar_wait(a_full + 0, par);
                         __syncwarp();
-                        issue45(a_st0, w_u0, BR, TAP, d_tile, false, Cfg::W_STREAM ? w_empty + 0 : nullptr, nullptr, nullptr);
+                        issue_step(IntTag<NOUT>(), IntTag<1>(), a_st0, w_u0, TAP, d_tile, false, vm, w_empty + 0, nullptr, nullptr);
                         // (3) A_hi x W_lo
-                        if (Cfg::W_STREAM || n == 0) tc::mbar_wait(w_full + 1, Cfg::W_STREAM ? par : 0u);
+                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) tc::mbar_wait(w_full + 1, par);
                         __syncwarp();
-                        issue45(a_st0, w_u1, BR, TAP, d_tile, false, a_empty + 0, Cfg::W_STREAM ? w_empty + 1 : nullptr,
-                                ks == KS - 1 ? acc_full + as : nullptr);
+                        issue_step(IntTag<NOUT>(), IntTag<1>(), a_st0, w_u1, TAP, d_tile, false, vm, a_empty + 0, w_empty + 1,
+                                   ks == KS - 1 ? acc_full + as : nullptr);
                     }
                 }
             }
@@ -334,15 +424,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                 for (int br = 0; br < 5; ++br) {
                     const int ch0 = br == 0 ? 0 : CO1 + (br - 1) * CO;
                     const int cnt = br == 0 ? CO1 : CO;
-                    uint32_t r[GW];
+                    uint32_t r[GW], r2[GW];
                     __syncwarp();    // tcgen05.ld is .sync.aligned: the lanes diverge on `valid` around the stores
-                    if constexpr (GW == 8) tc::tmem_ld8_nowait(t0 + (uint32_t)(br * NOUT + GW * G), r);
-                    else tc::tmem_ld4_nowait(t0 + (uint32_t)(br * NOUT + GW * G), r);
+                    if constexpr (GW == 8) tc::tmem_ld8_nowait(t0 + (uint32_t)(br * Cfg::NB + GW * G), r);
+                    else tc::tmem_ld4_nowait(t0 + (uint32_t)(br * Cfg::NB + GW * G), r);
+                    if constexpr (Cfg::MERGE) {      // lo-weight half of the accumulator pair
+                        if constexpr (GW == 8) tc::tmem_ld8_nowait(t0 + (uint32_t)(br * Cfg::NB + NOUT + GW * G), r2);
+                        else tc::tmem_ld4_nowait(t0 + (uint32_t)(br * Cfg::NB + NOUT + GW * G), r2);
+                    }
                     tc::tmem_ld_wait();
                     float o[GW], o2[GW];
 #pragma unroll
                     for (int jj = 0; jj < GW; ++jj) {
-                        const float d = __uint_as_float(r[jj]);
+                        const float d = Cfg::MERGE ? __uint_as_float(r[jj]) + __uint_as_float(r2[jj]) : __uint_as_float(r[jj]);
                         run[jj] = br <= 1 ? d : run[jj] + d;
                         o[jj] = 0.f; o2[jj] = 0.f;
                         if (GW * G + jj < cnt) {
