@@ -143,3 +143,36 @@ def test_split_path_multi_tile_per_cta_and_determinism(fold_sd):
     assert (lb[:3] - la).abs().max().item() <= LOGIT_TOL
     assert torch.equal(lb[147:150], lb[:3])
     assert torch.equal(m.segment(big, mean, std), mb)
+
+
+# ---- CTA pairs (cta_group::2 MMAs, kernels_tc_pair.cuh): option "tc_pair" ------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "f16tc"])
+@pytest.mark.parametrize("B,H,W", [(1, 8, 8), (1, 24, 40), (3, 72, 40), (1, 264, 328), (2, 512, 512)])
+def test_pair_kernels_bit_equal_single_cta(fold_sd, mode, B, H, W):
+    """Same fp16 products, same accumulation order: the M = 256 pair MMAs must reproduce the single-CTA kernels bit for
+    bit, including odd tile counts (one CTA of the last pair idles on a dummy tile) and partial tiles."""
+    sd = fold_sd(1)
+    mean, std = FOLD_MEAN_STD[1]
+    u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=11 * H + W, sigma=3.0)).to(DEV)
+    m = _model(sd, mode)
+    la, lb = torch.empty((B, 5, H, W), device=DEV), torch.empty((B, 5, H, W), device=DEV)
+    ma = m.set_option("tc_pair", 0).segment(u8, mean, std, logits=la).clone()
+    mb = m.set_option("tc_pair", 1).segment(u8, mean, std, logits=lb)
+    assert torch.equal(la, lb)
+    assert torch.equal(ma, mb)
+
+
+def test_pair_kernels_against_oracle_and_ring_wraparound(fold_sd):
+    """fp32 bar against the CPU oracle through the pair kernels, then many pair iterations per cluster."""
+    sd = fold_sd(3)
+    mean, std = FOLD_MEAN_STD[3]
+    u8 = O.synth_crops("D1", 2, 256, 256, seed=5)
+    ref = O.espnet_forward(sd, torch.from_numpy(O.normalise_bgr_u8(u8, mean, std)))
+    m = _model_split(sd).set_option("tc_pair", 1)
+    lg = torch.empty((2, 5, 256, 256), device=DEV)
+    m.segment(torch.from_numpy(u8).to(DEV), mean, std, logits=lg)
+    assert (lg.cpu() - ref).abs().max().item() <= LOGIT_TOL
+    big = torch.from_numpy(u8).to(DEV).repeat(75, 1, 1, 1)
+    lb = torch.empty((150, 5, 256, 256), device=DEV)
+    m.segment(big, mean, std, logits=lb)
+    assert torch.equal(lb[148:150], lg) and torch.equal(lb[:2], lg)
