@@ -6,15 +6,17 @@
 // the K-major chunk-plane A operand [kc][128 px][8 ch] (tc_common.cuh) -- the transpose is free because a thread owns a
 // pixel and writes one 16 B chunk per 8 channels.  The result leaves TMEM as fp16 chunk-plane o1h [B][kc][HW][8], the
 // layout the branch kernel's TMA box reads.  HBM-bound: 4*CIN + 2*8*NKC bytes per pixel.
-//   warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = loaders (pixel quarter x channel half),
-//   warps 12..15 = epilogue; A is double-buffered, accumulators are two tiles deep.
+//   warps 0..15 = loaders in TWO groups of 8 (pixel quarter x channel half): group g owns A stage g and the tiles of
+//   parity g, so two tiles' worth of global loads (2 x 64 KB at level 3) are in flight per SM -- one group's load latency
+//   hides the other's convert + store phase; warps 16..19 = epilogue, warp 20 = MMA issuer, warp 21 = TMEM allocator;
+//   accumulators are two tiles deep.
 #pragma once
 #include "kernels_fp32.cuh"
 #include "tc_common.cuh"
 
 namespace espnet {
 
-constexpr int kRedThreads = 512;
+constexpr int kRedThreads = 704;
 
 // SPLIT: fp32-equivalent variant, both operands as 3-term fp16 splits (see kernels_tc_branch.cuh): the A stage holds
 // [hi planes | lo planes], the weights [hi | lo], three MMAs per K step, and the result is written as the hi / lo
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
         }
         tc::mbar_fence_init();
     }
-    if (warp == 2) tc::tmem_alloc(tmem_slot, 64);
+    if (warp == 21) tc::tmem_alloc(tmem_slot, 64);
     for (int i = tid; i < Cfg::W_BYTES / 16; i += kRedThreads) reinterpret_cast<uint4*>(wbuf)[i] = __ldg(reinterpret_cast<const uint4*>(w) + i);
     tc::fence_proxy_async();
     tc::tc_fence_before();
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 1) {
+    if (warp == 20) {
         // ===== MMA issuer: converged warp, one elected lane issues (tc_common.cuh: elect_one) =====
         {
             constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
@@ -130,11 +132,12 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
                 __syncwarp();
             }
         }
-    } else if (warp >= 4 && warp < 12) {
-        // ===== loaders: warp lw -> pixels 32*(lw%4) + lane, K chunks [(lw/4) * KC/2, +KC/2) =====
-        const int lw = warp - 4, px = 32 * (lw & 3) + lane, kc0 = (lw >> 2) * (KC / 2);
+    } else if (warp < 16) {
+        // ===== loaders: group = warp / 8 (tiles of that parity), warp lw of the group -> pixels 32*(lw%4) + lane,
+        // K chunks [(lw/4) * KC/2, +KC/2) =====
+        const int lw = warp & 7, px = 32 * (lw & 3) + lane, kc0 = (lw >> 2) * (KC / 2);
         const uint32_t plane_b = (uint32_t)HW * 4u;
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int it = warp >> 3; it < my_tiles; it += 2) {
             const int t_lin = (int)blockIdx.x + it * (int)gridDim.x;
             const int tile = reverse ? total_tiles - 1 - t_lin : t_lin;     // see the launcher: walk against the producer's order
             const int b = tile / chunks, p = (tile % chunks) * 128 + px;
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(a_full + s);
         }
-    } else if (warp >= 12) {
+    } else if (warp < 20) {
         // ===== epilogue: TMEM -> fp16 chunk-plane o1h =====
         const int q = warp & 3, px = 32 * q + lane;
         for (int it = 0; it < my_tiles; ++it) {
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem_base, 64);
+    if (warp == 21) tc::tmem_dealloc(tmem_base, 64);
 }
 
 }  // namespace espnet
