@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
             const int tile = reverse ? total_tiles - 1 - t_lin : t_lin;
             const int b = tile / chunks, p = (tile % chunks) * 128 + px;
             const int s = it & 1;
-            tc::mbar_wait(acc_full + s, (uint32_t)((it >> 1) & 1));
+            tc::mbar_wait_backoff(acc_full + s, (uint32_t)((it >> 1) & 1));
             tc::tc_fence_after();
             float v[NOUT];
             const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * 32);

@@ -43,6 +43,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+// the same for a warp that is NOT on the critical path (e.g. an epilogue that waits a whole tile): sleep between polls so
+// that the spin loop does not take issue slots from the warps that feed the pipeline
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
+
 // ---- async-proxy copies ------------------------------------------------------------------------------------------
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
