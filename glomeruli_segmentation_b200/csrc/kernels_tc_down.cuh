@@ -160,20 +160,32 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
             }
         }
         const int total = my_tiles * KS;
+        // The loaders are instruction-bound (ncu: ~24 SASS instructions per loaded value with naive pointer arithmetic), so
+        // addresses are a per-crop 64-bit base + ONE IMAD.WIDE.U32 per load (32-bit plane stride x constant channel index;
+        // the host guarantees CIN * Hi * Wi * 4 < 2^32), and the channel bound is only tested in the last, partial K step.
+        const uint32_t plane_b = (uint32_t)(iplane * sizeof(float));
         auto issue = [&](int c, float (&v)[NT][8]) {
             const int it = c / KS, ks = c - it * KS;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
             const int y_in0 = 2 * (ty * 16) - 1, x_in0 = 2 * (tx * 8) - 1;
-            const float* src_b = in + (size_t)b * CIN * iplane;
+            const char* src_b = reinterpret_cast<const char*>(in + (size_t)b * CIN * iplane);
+            const bool full = 16 * ks + 16 <= CIN;              // warp-uniform: every channel of this K step exists
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
                 const int yi = y_in0 + rr[i], xi = x_in0 + cq[i];
                 const bool inb = soff[i] >= 0 && yi >= 0 && yi < Hi && xi >= 0 && xi < Wi;
                 const int ch0 = 16 * ks + 8 * kk[i];
-                const float* sp = src_b + (size_t)ch0 * iplane + (inb ? yi * Wi + xi : 0);
+                const char* sp = src_b + (uint64_t)plane_b * (uint32_t)ch0 + (uint32_t)((inb ? yi * Wi + xi : 0) * 4);
+                if (full) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[i][j] = (inb && ch0 + j < CIN) ? __ldg(sp + (size_t)j * iplane) : 0.f;
+                    for (int j = 0; j < 8; ++j)
+                        v[i][j] = inb ? __ldg(reinterpret_cast<const float*>(sp + (uint64_t)plane_b * (uint32_t)j)) : 0.f;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        v[i][j] = (inb && ch0 + j < CIN) ? __ldg(reinterpret_cast<const float*>(sp + (uint64_t)plane_b * (uint32_t)j)) : 0.f;
+                }
             }
         };
         auto store = [&](int c, const float (&v)[NT][8]) {
