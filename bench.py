@@ -59,7 +59,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.begin = index, None, [], 0
 
     def start(self):
         try:
@@ -73,6 +73,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, timeout=5.0):
+        """Call right before the timed region: waits until nvidia-smi delivers (its start-up takes longer than a short
+        timed region) and discards what was sampled before."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.begin = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -80,7 +90,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in (self.lines[self.begin:] or self.lines):
             f = [t.strip() for t in l.split(",")]
             if len(f) < 6:
                 continue
@@ -311,11 +321,15 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.mark()
+        step_resident()         # the GPU idled while nvidia-smi started up
     l0 = _lib.lib().espnet_launch_count()
     ms = timed(step_resident, args.steps)
     launches = int(_lib.lib().espnet_launch_count() - l0)
@@ -467,6 +481,7 @@ def run_wsi(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = _lib.lib().espnet_launch_count()

@@ -67,8 +67,23 @@ SYMBOLS = {
 _lib = None
 
 
-def build(verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+def _up_to_date() -> bool:
+    """make-style check: the library exists and is newer than every source it is built from"""
+    if not os.path.isfile(LIB_PATH):
+        return False
+    t = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc")) if f.endswith((".cu", ".cuh", ".h", ".sh"))]
+    inc = os.path.join(os.path.dirname(_HERE), "include")
+    srcs += [os.path.join(inc, f) for f in os.listdir(inc)] if os.path.isdir(inc) else []
+    return all(os.path.getmtime(f) <= t for f in srcs)
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU; one translation unit, ~3 min).
+    Like make, nothing is recompiled when the library is newer than all of its sources (force=True or
+    ESPNET_B200_REBUILD=1 recompiles anyway)."""
+    if not force and not os.environ.get("ESPNET_B200_REBUILD") and _up_to_date():
+        return LIB_PATH
     script = os.path.join(_HERE, "csrc", "build.sh")
     r = subprocess.run(["bash", script], capture_output=True, text=True)
     if r.returncode != 0:
