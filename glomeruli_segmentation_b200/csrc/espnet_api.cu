@@ -737,7 +737,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         if (!full) {
             h->stages["encoder.classifier"] = {p.enc_out, (size_t)B * NC * H8 * W8};
             if (a->mask) {
-                dim3 g((W + 31) / 32, (H + 7) / 8, B);
+                dim3 g((W / 4 + 31) / 32, (H + 7) / 8, B);     // one thread = 4 output pixels
                 { ProfScope _ps(h, "upsample8_argmax", st); upsample8_argmax_kernel<NC><<<g, 256, 0, st>>>(p.enc_out, B, H8, W8, a->mask, nullptr); }
                 LAUNCH_COUNT();
                 CUDA_TRY(h, cudaPeekAtLastError());

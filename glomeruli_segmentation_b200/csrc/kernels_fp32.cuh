@@ -990,32 +990,59 @@ __global__ void __launch_bounds__(256) dec_c_kernel(const DecCParams<NC> p) {
 
 // ESPNet-C tail: nn.Upsample(scale_factor=8, mode='bilinear', align_corners=False)
 // (VisualizeResults_iou.py:258-261,125-126) + arg-max (:128) of encoder logits [B,NC,H8,W8].
+// One thread = 4 horizontally adjacent output pixels (a uchar4 / float4 store): they read at most 3 source columns, which
+// are loaded once; the interpolation arithmetic per pixel is unchanged (same operations, same order).
 template <int NC>
 __global__ void __launch_bounds__(256) upsample8_argmax_kernel(const float* __restrict__ enc, int B, int H8, int W8,
                                                                unsigned char* __restrict__ mask, float* __restrict__ up_logits) {
     const int H = 8 * H8, W = 8 * W8;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int xg = 4 * (blockIdx.x * 32 + (threadIdx.x & 31));
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int b = blockIdx.z;
-    if (x >= W || y >= H) return;
+    if (xg >= W || y >= H) return;
     // area_pixel_compute_source_index(scale=1/8, align_corners=False): src = (dst+0.5)/8-0.5, clamped at 0
     float sy = 0.125f * ((float)y + 0.5f) - 0.5f; sy = sy < 0.f ? 0.f : sy;
-    float sx = 0.125f * ((float)x + 0.5f) - 0.5f; sx = sx < 0.f ? 0.f : sx;
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < H8 - 1 ? 1 : 0), x1 = x0 + (x0 < W8 - 1 ? 1 : 0);
+    const int y0 = (int)sy;
+    const int y1 = y0 + (y0 < H8 - 1 ? 1 : 0);
     const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
-    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+    int x0[4]; float lx1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float sx = 0.125f * ((float)(xg + j) + 0.5f) - 0.5f; sx = sx < 0.f ? 0.f : sx;
+        x0[j] = (int)sx;
+        lx1[j] = sx - (float)x0[j];
+    }
+    // source columns c0 = x0[0], c0 + 1, c0 + 2 (clamped): x0[j] is c0 or c0 + 1, its right neighbour min(x0[j] + 1, W8 - 1)
+    const int c0 = x0[0], c1 = min(c0 + 1, W8 - 1), c2 = min(c0 + 2, W8 - 1);
     const size_t plane = (size_t)H8 * W8;
-    float v[NC];
+    float v[4][NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const float* s = enc + ((size_t)b * NC + c) * plane;
-        const float v00 = __ldg(s + (size_t)y0 * W8 + x0), v01 = __ldg(s + (size_t)y0 * W8 + x1);
-        const float v10 = __ldg(s + (size_t)y1 * W8 + x0), v11 = __ldg(s + (size_t)y1 * W8 + x1);
-        v[c] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-        if (up_logits) up_logits[((size_t)b * NC + c) * H * W + (size_t)y * W + x] = v[c];
+        const float* r0 = s + (size_t)y0 * W8;
+        const float* r1 = s + (size_t)y1 * W8;
+        const float a0 = __ldg(r0 + c0), a1 = __ldg(r0 + c1), a2 = __ldg(r0 + c2);
+        const float b0 = __ldg(r1 + c0), b1 = __ldg(r1 + c1), b2 = __ldg(r1 + c2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool sh = x0[j] != c0;
+            const float v00 = sh ? a1 : a0, v01 = sh ? a2 : a1, v10 = sh ? b1 : b0, v11 = sh ? b2 : b1;
+            const float lx0 = 1.f - lx1[j];
+            v[j][c] = ly0 * (lx0 * v00 + lx1[j] * v01) + ly1 * (lx0 * v10 + lx1[j] * v11);
+        }
+        if (up_logits) {
+            float* d = up_logits + ((size_t)b * NC + c) * H * W + (size_t)y * W + xg;
+            if ((reinterpret_cast<uintptr_t>(up_logits) & 15) == 0) *reinterpret_cast<float4*>(d) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
+            else { d[0] = v[0][c]; d[1] = v[1][c]; d[2] = v[2][c]; d[3] = v[3][c]; }
+        }
     }
-    if (mask) mask[(size_t)b * H * W + (size_t)y * W + x] = (unsigned char)argmax_first<NC>(v);
+    if (mask) {
+        unsigned char* d = mask + (size_t)b * H * W + (size_t)y * W + xg;
+        const uchar4 m4 = make_uchar4((unsigned char)argmax_first<NC>(v[0]), (unsigned char)argmax_first<NC>(v[1]),
+                                      (unsigned char)argmax_first<NC>(v[2]), (unsigned char)argmax_first<NC>(v[3]));
+        if ((reinterpret_cast<uintptr_t>(mask) & 3) == 0) *reinterpret_cast<uchar4*>(d) = m4;     // caller buffers may be unaligned views
+        else { d[0] = m4.x; d[1] = m4.y; d[2] = m4.z; d[3] = m4.w; }
+    }
 }
 
 }  // namespace espnet
