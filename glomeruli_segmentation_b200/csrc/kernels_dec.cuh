@@ -12,10 +12,15 @@ namespace espnet {
 template <int NC>
 __global__ void __launch_bounds__(256) dec_c4_kernel(const DecCParams<NC> p) {
     constexpr int CI = NC + 19;
-    __shared__ float sw[CI * 9 * NC];
+    // weights of one (input channel, tap row): 3 kx x NC values padded to WR floats -> LDS.128 broadcasts
+    constexpr int WR = (3 * NC + 3) & ~3;
+    __shared__ __align__(16) float sw[CI * 3 * WR];
     __shared__ float swt[NC * NC * 4];
     __shared__ float sb[3 * NC];
-    for (int i = threadIdx.x; i < CI * 9 * NC; i += 256) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < CI * 3 * WR; i += 256) {
+        const int r = i / WR, k = i - r * WR;
+        sw[i] = k < 3 * NC ? p.w[r * 3 * NC + k] : 0.f;
+    }
     for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
     for (int i = threadIdx.x; i < NC; i += 256) { sb[i] = p.s[i]; sb[NC + i] = p.t[i]; sb[2 * NC + i] = p.a[i]; }
     __syncthreads();
@@ -44,7 +49,12 @@ __global__ void __launch_bounds__(256) dec_c4_kernel(const DecCParams<NC> p) {
             in[0] = has_l ? __ldg(row - 1) : 0.f;
             in[1] = c.x; in[2] = c.y; in[3] = c.z; in[4] = c.w;
             in[5] = has_r ? __ldg(row + 4) : 0.f;
-            const float* wr = sw + (ci * 9 + ky * 3) * NC;
+            float wr[WR];
+#pragma unroll
+            for (int k = 0; k < WR / 4; ++k) {
+                const float4 w4 = *reinterpret_cast<const float4*>(sw + (ci * 3 + ky) * WR + 4 * k);
+                wr[4 * k] = w4.x; wr[4 * k + 1] = w4.y; wr[4 * k + 2] = w4.z; wr[4 * k + 3] = w4.w;
+            }
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
