@@ -56,13 +56,17 @@ __global__ void __launch_bounds__(256) dec_c4_kernel(const DecCParams<NC> p) {
                 wr[4 * k] = w4.x; wr[4 * k + 1] = w4.y; wr[4 * k + 2] = w4.z; wr[4 * k + 3] = w4.w;
             }
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
+            for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-                for (int j = 0; j < NC; ++j) {
-                    const float wv = wr[kx * NC + j];
+                for (int j = 0; j + 1 < NC; j += 2)       // class pairs: one packed FFMA2 per pixel
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q][j] = fmaf(in[q + kx], wv, acc[q][j]);
+                    for (int q = 0; q < 4; ++q) ffma2(acc[q][j], acc[q][j + 1], in[q + kx], wr[kx * NC + j], wr[kx * NC + j + 1]);
+                if (NC & 1) {
+                    const float wv = wr[kx * NC + NC - 1];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q][NC - 1] = fmaf(in[q + kx], wv, acc[q][NC - 1]);
                 }
+            }
         }
     }
     const int W = 2 * W2;

@@ -66,6 +66,17 @@ __device__ __forceinline__ void fma_tile(float (&acc)[kRows][CO], const float (&
 
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 
+// d0 = fma(a, b0, d0), d1 = fma(a, b1, d1) as ONE packed instruction (sm_100 FFMA2 with a broadcast scalar operand): two
+// IEEE fp32 FMAs, bit-identical to two fmaf, half the issue slots -- for the issue-bound CUDA-core convolutions.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+    unsigned long long d, av, bv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(av), "l"(bv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 __device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict__ src, int n) {
     // n is a multiple of 4 and both pointers are 16 B aligned (the packer guarantees it)
     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -235,14 +246,10 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 w = w4[j4];
-                acc[0][4 * j4 + 0] = fmaf(a0, w.x, acc[0][4 * j4 + 0]);
-                acc[0][4 * j4 + 1] = fmaf(a0, w.y, acc[0][4 * j4 + 1]);
-                acc[0][4 * j4 + 2] = fmaf(a0, w.z, acc[0][4 * j4 + 2]);
-                acc[0][4 * j4 + 3] = fmaf(a0, w.w, acc[0][4 * j4 + 3]);
-                acc[1][4 * j4 + 0] = fmaf(a1, w.x, acc[1][4 * j4 + 0]);
-                acc[1][4 * j4 + 1] = fmaf(a1, w.y, acc[1][4 * j4 + 1]);
-                acc[1][4 * j4 + 2] = fmaf(a1, w.z, acc[1][4 * j4 + 2]);
-                acc[1][4 * j4 + 3] = fmaf(a1, w.w, acc[1][4 * j4 + 3]);
+                ffma2(acc[0][4 * j4 + 0], acc[0][4 * j4 + 1], a0, w.x, w.y);
+                ffma2(acc[0][4 * j4 + 2], acc[0][4 * j4 + 3], a0, w.z, w.w);
+                ffma2(acc[1][4 * j4 + 0], acc[1][4 * j4 + 1], a1, w.x, w.y);
+                ffma2(acc[1][4 * j4 + 2], acc[1][4 * j4 + 3], a1, w.z, w.w);
             }
         }
         pool[0][c] = s0 / 9.f;                                            // count_include_pad: always / 9
