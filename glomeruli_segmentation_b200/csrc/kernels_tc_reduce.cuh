@@ -29,6 +29,24 @@ __device__ __forceinline__ void split_f16x2(float a, float b, __half2& hi, __hal
     const float2 hf = __half22float2(hi);
     lo = __floats2half2_rn(sa - hf.x, sb - hf.y);
 }
+// the same with the scale and the remainder as packed fp32x2 instructions (FMUL2 / FADD2, bit-identical): 6 instead of 8
+// instructions per pair where the two inputs already sit in an aligned register pair (the 1x1 reduce loaders: measured
+// 0.45 -> 0.43 ms; in the 3x3-s2 loaders the pairing costs moves and is slower)
+__device__ __forceinline__ void split_f16x2_packed(float a, float b, __half2& hi, __half2& lo) {
+    unsigned long long v, s, h, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(s) : "f"(kSplitScaleA));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(v), "l"(s));
+    float sa, sb;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(v));
+    hi = __floats2half2_rn(sa, sb);
+    const float2 hf = __half22float2(hi);
+    asm("mov.b64 %0, {%1, %2};" : "=l"(h) : "f"(hf.x), "f"(hf.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(v), "l"(h));
+    float da, db;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(da), "=f"(db) : "l"(d));
+    lo = __floats2half2_rn(da, db);
+}
 
 template <int CIN, int NOUT, bool SPLIT = false>
 struct ReduceTcCfg {
@@ -158,7 +176,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
                 __half2 h[4], l[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if constexpr (SPLIT) split_f16x2(v[k][2 * j], v[k][2 * j + 1], h[j], l[j]);
+                    if constexpr (SPLIT) split_f16x2_packed(v[k][2 * j], v[k][2 * j + 1], h[j], l[j]);
                     else h[j] = __floats2half2_rn(v[k][2 * j], v[k][2 * j + 1]);
                 }
                 uint4 u;
