@@ -176,3 +176,23 @@ def test_pair_kernels_against_oracle_and_ring_wraparound(fold_sd):
     lb = torch.empty((150, 5, 256, 256), device=DEV)
     m.segment(big, mean, std, logits=lb)
     assert torch.equal(lb[148:150], lg) and torch.equal(lb[:2], lg)
+
+
+def test_random_shapes_all_paths_agree(fold_sd):
+    """Seeded sweep over odd crop geometries (partial MMA tiles in both directions, one-tile maps, odd tile counts):
+    tensor-core split path vs the CUDA-core fp32 path within the fp32 bar, CTA-pair kernels bit-equal to single-CTA."""
+    sd = fold_sd(5)
+    mean, std = FOLD_MEAN_STD[5]
+    rng = np.random.default_rng(2024)
+    m_cc = _model(sd, "fp32").set_option("fp32_impl", 0)
+    m_tc = _model_split(sd)
+    for _ in range(10):
+        B = int(rng.integers(1, 4))
+        H, W = 8 * int(rng.integers(1, 48)), 8 * int(rng.integers(1, 48))
+        u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=int(rng.integers(1 << 30)), sigma=3.0)).to(DEV)
+        l0, l1, l2 = (torch.empty((B, 5, H, W), device=DEV) for _ in range(3))
+        m_cc.segment(u8, mean, std, logits=l0)
+        m_tc.set_option("tc_pair", 0).segment(u8, mean, std, logits=l1)
+        m_tc.set_option("tc_pair", 1).segment(u8, mean, std, logits=l2)
+        assert (l1 - l0).abs().max().item() <= LOGIT_TOL, (B, H, W)
+        assert torch.equal(l1, l2), (B, H, W)
