@@ -776,7 +776,14 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         const size_t n = (size_t)B * H4 * W4;
         int grid = (int)((n + 255) / 256);
         if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
-        { ProfScope _ps(h, "dec_b", st); dec_b_kernel<NC><<<grid, 256, 0, st>>>(p); }
+        // 4 pixels per thread (kernels_dec.cuh) when the vector loads / stores are aligned
+        const bool b4 = NC == 5 && h->dec_impl != 0 && (W4 % 4 == 0) && (((uintptr_t)p.tin | (uintptr_t)p.comb) % 16 == 0);
+        if (b4) {
+            dim3 g4((W4 / 4 + 31) / 32, (H4 + 7) / 8, B);
+            { ProfScope _ps(h, "dec_b", st); dec_b4_kernel<NC><<<g4, 256, 0, st>>>(p); }
+        } else {
+            ProfScope _ps(h, "dec_b", st); dec_b_kernel<NC><<<grid, 256, 0, st>>>(p);
+        }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         h->stages["up_l2"] = {ws + L.comb, (size_t)B * NC * H2 * W2};

@@ -271,4 +271,98 @@ __global__ void __launch_bounds__(256) dec_av_kernel(const DecAParams<NC> p) {
     }
 }
 
+// S9, register-tiled like dec_c4_kernel: combine_l2_l3 CBR 3x3 2NC->NC (Model.py:330,373) + up_l2 ConvT k2 s2 + BR
+// (Model.py:335,374) -> comb [B,NC,H2,W2].  One thread owns FOUR consecutive quarter-resolution pixels: per (input channel,
+// tap row) 3 loads (one 16 B vector + the two neighbours) and 4 LDS.128 weight broadcasts feed 12 NC FMAs (the one-pixel
+// dec_b_kernel issues one scalar LDS per FMA and is LSU-bound), and each class row leaves as two 16 B stores.
+template <int NC>
+__global__ void __launch_bounds__(256) dec_b4_kernel(const DecBParams<NC> p) {
+    constexpr int CI = 2 * NC;
+    constexpr int WR = (3 * NC + 3) & ~3;
+    __shared__ __align__(16) float sw[CI * 3 * WR];
+    __shared__ float swt[NC * NC * 4];
+    __shared__ float sb[6 * NC];
+    for (int i = threadIdx.x; i < CI * 3 * WR; i += 256) {
+        const int r = i / WR, k = i - r * WR;
+        sw[i] = k < 3 * NC ? p.w[r * 3 * NC + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
+    for (int i = threadIdx.x; i < NC; i += 256) {
+        sb[i] = p.s[i]; sb[NC + i] = p.t[i]; sb[2 * NC + i] = p.a[i];
+        sb[3 * NC + i] = p.s2[i]; sb[4 * NC + i] = p.t2[i]; sb[5 * NC + i] = p.a2[i];
+    }
+    __syncthreads();
+    const int H4 = p.H4, W4 = p.W4;
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x0 >= W4 || y >= H4) return;
+    const size_t plane = (size_t)H4 * W4;
+    float acc[4][NC];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[q][j] = 0.f;
+    const bool has_l = x0 > 0, has_r = x0 + 4 < W4;
+#pragma unroll 1
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H4) continue;                 // zero padding row (uniform per warp)
+        const float* rowb = p.tin + (size_t)b * CI * plane + (size_t)yy * W4 + x0;
+#pragma unroll 2
+        for (int ci = 0; ci < CI; ++ci) {
+            const float* row = rowb + (size_t)ci * plane;
+            const float4 c = __ldg(reinterpret_cast<const float4*>(row));
+            float in[6];
+            in[0] = has_l ? __ldg(row - 1) : 0.f;
+            in[1] = c.x; in[2] = c.y; in[3] = c.z; in[4] = c.w;
+            in[5] = has_r ? __ldg(row + 4) : 0.f;
+            float wr[WR];
+#pragma unroll
+            for (int k = 0; k < WR / 4; ++k) {
+                const float4 w4 = *reinterpret_cast<const float4*>(sw + (ci * 3 + ky) * WR + 4 * k);
+                wr[4 * k] = w4.x; wr[4 * k + 1] = w4.y; wr[4 * k + 2] = w4.z; wr[4 * k + 3] = w4.w;
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const float wv = wr[kx * NC + j];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q][j] = fmaf(in[q + kx], wv, acc[q][j]);
+                }
+        }
+    }
+    const int W2 = 2 * W4;
+    const size_t plane2 = 4 * plane;
+    float v[4][NC];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[q][j] = bn_prelu(acc[q][j], sb[j], sb[NC + j], sb[2 * NC + j]);
+#pragma unroll
+    for (int o = 0; o < NC; ++o) {
+        float r0[8], r1[8];            // two output rows x 8 consecutive half-resolution pixels
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float* wq = swt + (c * NC + o) * 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r[k] = fmaf(v[q][c], wq[k], r[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = bn_prelu(r[k], sb[3 * NC + o], sb[4 * NC + o], sb[5 * NC + o]);
+            r0[2 * q] = r[0]; r0[2 * q + 1] = r[1];
+            r1[2 * q] = r[2]; r1[2 * q + 1] = r[3];
+        }
+        float* d = p.comb + ((size_t)b * NC + o) * plane2 + (size_t)(2 * y) * W2 + 2 * x0;
+        *reinterpret_cast<float4*>(d) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(r0[4], r0[5], r0[6], r0[7]);
+        *reinterpret_cast<float4*>(d + W2) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+        *reinterpret_cast<float4*>(d + W2 + 4) = make_float4(r1[4], r1[5], r1[6], r1[7]);
+    }
+}
+
 }  // namespace espnet
