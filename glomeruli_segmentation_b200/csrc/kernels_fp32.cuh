@@ -158,67 +158,39 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
-        // u8 HWC rows: 195 contiguous bytes per region row, fetched as aligned 32-bit words
+        // u8 HWC: one task = one region pixel (3 consecutive bytes, a warp reads 96 contiguous bytes per load); all byte
+        // loads of a thread are issued first (phase 1), then table look-ups and the parity-split stores (phase 2)
         const unsigned char* x = reinterpret_cast<const unsigned char*>(p.x);
         long long ox = 0, oy = 0, pitch_px = p.W, rows = p.H, row0 = (long long)b * p.H;
         if (FMT == 2) { ox = p.origins[2 * b]; oy = p.origins[2 * b + 1]; pitch_px = p.slide_w; rows = p.slide_h; row0 = 0; }
-        const size_t total = FMT == 2 ? (size_t)p.slide_h * p.slide_w * 3 : (size_t)p.B * p.H * p.W * 3;
-        constexpr int kWordsPerRow = (kStemRW * 3 + 3 + 3) / 4;     // 195 bytes + up to 3 bytes of misalignment
-        constexpr int kRowsPerWarp = (kStemRH + 7) / 8, kWordsPerLane = (kWordsPerRow + 31) / 32;
-        // phase 1: every word this thread is responsible for (one warp per region row), all loads in flight at once
-        unsigned int words[kRowsPerWarp][kWordsPerLane];
+        constexpr int kPix = kStemRH * kStemRW, kIters = (kPix + 255) / 256;
+        unsigned int bgr[kIters];        // b | g << 8 | r << 16, bit 24 = pixel is inside the crop (else zero padding)
 #pragma unroll
-        for (int ri = 0; ri < kRowsPerWarp; ++ri) {
-            const int r = (tid >> 5) + 8 * ri;
-            const int yy = ry0 + r;
-            const long long sy = oy + yy;                            // row in the source image
-            const bool row_ok = r < kStemRH && yy >= 0 && yy < p.H && sy >= 0 && sy < rows;
-            // byte address of region column 0 in this row (may be negative / outside: only used for alignment and bounds)
-            const long long a0 = ((row0 + sy) * pitch_px + (ox + rx0)) * 3;
-#pragma unroll
-            for (int k = 0; k < kWordsPerLane; ++k) {
-                const int wi = (tid & 31) + 32 * k;
-                const long long aw = ((a0 >> 2) + wi) << 2;          // aligned word address (arithmetic shift floors)
-                unsigned int word = 0;
-                if (row_ok && wi < kWordsPerRow && aw >= 0 && (size_t)aw < total) {
-                    if ((size_t)aw + 4 <= total) word = __ldg(reinterpret_cast<const unsigned int*>(x + aw));
-                    else for (int q = 0; q < 4 && (size_t)aw + q < total; ++q) word |= (unsigned int)x[aw + q] << (8 * q);
+        for (int i = 0; i < kIters; ++i) {
+            const int t = tid + 256 * i;
+            const int r = t / kStemRW, j = t - r * kStemRW;
+            const int yy = ry0 + r, xx = rx0 + j;
+            unsigned int u = 0;
+            if (t < kPix && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+                u = 1u << 24;
+                const long long sy = oy + yy, sx = ox + xx;
+                // outside the slide openslide pads with 0 (then normalised like any pixel)
+                if (sy >= 0 && sy < rows && sx >= 0 && sx < pitch_px) {
+                    const unsigned char* q = x + ((row0 + sy) * pitch_px + sx) * 3;
+                    u |= (unsigned int)__ldg(q) | ((unsigned int)__ldg(q + 1) << 8) | ((unsigned int)__ldg(q + 2) << 16);
                 }
-                words[ri][k] = word;
             }
+            bgr[i] = u;
         }
-        // phase 2: bytes -> (pixel, channel) -> table -> shared memory
 #pragma unroll
-        for (int ri = 0; ri < kRowsPerWarp; ++ri) {
-            const int r = (tid >> 5) + 8 * ri;
-            if (r >= kStemRH) continue;
-            const int yy = ry0 + r;
-            const long long sy = oy + yy;
-            const bool row_in_crop = yy >= 0 && yy < p.H;
-            const bool row_in_src = sy >= 0 && sy < rows;
-            const long long a0 = ((row0 + sy) * pitch_px + (ox + rx0)) * 3;
-            const int lead = (int)(a0 - ((a0 >> 2) << 2));           // bytes of the first word before region column 0
+        for (int i = 0; i < kIters; ++i) {
+            const int t = tid + 256 * i;
+            if (t >= kPix) continue;
+            const int r = t / kStemRW, j = t - r * kStemRW;
+            const unsigned int u = bgr[i];
+            const bool in_crop = (u >> 24) != 0;
 #pragma unroll
-            for (int k = 0; k < kWordsPerLane; ++k) {
-                const int wi = (tid & 31) + 32 * k;
-                if (wi >= kWordsPerRow) continue;
-                const unsigned int word = words[ri][k];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int off = 4 * wi - lead + q;               // byte offset inside the region row
-                    if (off < 0 || off >= kStemRW * 3) continue;
-                    const int j = (off * 171) >> 9, c = off - 3 * j; // off / 3 for off < 256
-                    const int xx = rx0 + j;
-                    const long long sx = ox + xx;
-                    float v = 0.f;                                   // zero padding of the normalised tensor
-                    if (row_in_crop && xx >= 0 && xx < p.W) {
-                        // outside the slide openslide pads with 0 (then normalised like any pixel)
-                        const unsigned int u = (row_in_src && sx >= 0 && sx < pitch_px) ? ((word >> (8 * q)) & 255u) : 0u;
-                        v = lut[c * 256 + u];
-                    }
-                    put(c, r, j, v);
-                }
-            }
+            for (int c = 0; c < 3; ++c) put(c, r, j, in_crop ? lut[c * 256 + ((u >> (8 * c)) & 255u)] : 0.f);
         }
     }
     __syncthreads();
