@@ -925,8 +925,12 @@ __global__ void __launch_bounds__(256) dec_c_kernel(const DecCParams<NC> p) {
 #pragma unroll
         for (int o = 0; o < NC; ++o) {
             float* d = p.logits + ((size_t)b * NC + o) * fplane + base;
-            *reinterpret_cast<float2*>(d) = make_float2(lg[0][o], lg[1][o]);
-            *reinterpret_cast<float2*>(d + W) = make_float2(lg[2][o], lg[3][o]);
+            if ((reinterpret_cast<uintptr_t>(p.logits) & 7) == 0) {     // caller buffers may be 4-byte-offset views
+                *reinterpret_cast<float2*>(d) = make_float2(lg[0][o], lg[1][o]);
+                *reinterpret_cast<float2*>(d + W) = make_float2(lg[2][o], lg[3][o]);
+            } else {
+                d[0] = lg[0][o]; d[1] = lg[1][o]; d[W] = lg[2][o]; d[W + 1] = lg[3][o];
+            }
         }
     }
     int am[4];
@@ -949,11 +953,19 @@ __global__ void __launch_bounds__(256) dec_c_kernel(const DecCParams<NC> p) {
 #pragma unroll
         for (int o = 0; o < NC; ++o) {
             float* d = p.prob_acc + ((size_t)b * NC + o) * fplane + base;
+            const bool al8 = (reinterpret_cast<uintptr_t>(p.prob_acc) & 7) == 0;
             float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
-            if (!p.prob_init) { t0 = *reinterpret_cast<float2*>(d); t1 = *reinterpret_cast<float2*>(d + W); }
+            if (!p.prob_init) {
+                if (al8) { t0 = *reinterpret_cast<float2*>(d); t1 = *reinterpret_cast<float2*>(d + W); }
+                else { t0 = make_float2(d[0], d[1]); t1 = make_float2(d[W], d[W + 1]); }
+            }
             pr[0][o] += t0.x; pr[1][o] += t0.y; pr[2][o] += t1.x; pr[3][o] += t1.y;
-            *reinterpret_cast<float2*>(d) = make_float2(pr[0][o], pr[1][o]);
-            *reinterpret_cast<float2*>(d + W) = make_float2(pr[2][o], pr[3][o]);
+            if (al8) {
+                *reinterpret_cast<float2*>(d) = make_float2(pr[0][o], pr[1][o]);
+                *reinterpret_cast<float2*>(d + W) = make_float2(pr[2][o], pr[3][o]);
+            } else {
+                d[0] = pr[0][o]; d[1] = pr[1][o]; d[W] = pr[2][o]; d[W + 1] = pr[3][o];
+            }
         }
         if (p.mask_from_prob) {
 #pragma unroll
@@ -962,8 +974,13 @@ __global__ void __launch_bounds__(256) dec_c_kernel(const DecCParams<NC> p) {
     }
     if (p.mask) {
         unsigned char* d = p.mask + (size_t)b * fplane + base;
-        *reinterpret_cast<uchar2*>(d) = make_uchar2((unsigned char)am[0], (unsigned char)am[1]);
-        *reinterpret_cast<uchar2*>(d + W) = make_uchar2((unsigned char)am[2], (unsigned char)am[3]);
+        if ((reinterpret_cast<uintptr_t>(p.mask) & 1) == 0) {        // W and base are even; caller buffers may be odd-offset views
+            *reinterpret_cast<uchar2*>(d) = make_uchar2((unsigned char)am[0], (unsigned char)am[1]);
+            *reinterpret_cast<uchar2*>(d + W) = make_uchar2((unsigned char)am[2], (unsigned char)am[3]);
+        } else {
+            d[0] = (unsigned char)am[0]; d[1] = (unsigned char)am[1];
+            d[W] = (unsigned char)am[2]; d[W + 1] = (unsigned char)am[3];
+        }
     }
 }
 

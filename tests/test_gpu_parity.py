@@ -256,3 +256,37 @@ def test_gpu_confusion_histogram_matches_reference_ioueval():
     big_g = torch.randint(0, 5, (3_000_000,), dtype=torch.uint8, device=DEV)
     ev2 = iouEval(5)
     assert np.array_equal(ev2.addBatch(big_p, big_g), W.fast_hist(big_g.cpu().numpy(), big_p.cpu().numpy(), 5))
+
+
+@pytest.mark.parametrize("net", ["full", "encoder"])
+def test_unaligned_caller_buffers(fold_sd, net):
+    """Input crops and output masks that are byte-offset views (no 4 / 8 / 16 B alignment): the vectorised stores fall back
+    to scalar ones and the stem's byte loads do not care -- same masks as with aligned buffers."""
+    from glomeruli_segmentation_b200 import ESPNet_Encoder
+    sd = fold_sd(1)
+    mean, std = FOLD_MEAN_STD[1]
+    if net == "full":
+        m = ESPNet(5, 2, 8); m.load_state_dict(sd, strict=True)
+    else:
+        m = ESPNet_Encoder(5, 2, 8); m.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    m = m.to(DEV).eval()
+    B, H, W = 2, 72, 104
+    u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=77, sigma=3.0)).to(DEV)
+    lg_shape = (B, 5, H, W) if net == "full" else (B, 5, H // 8, W // 8)      # the encoder returns 1/8-resolution logits
+    ref_lg = torch.empty(lg_shape, device=DEV)
+    ref = m.segment(u8, mean, std, logits=ref_lg).clone()
+    for off in (1, 2, 3, 5):
+        raw_in = torch.empty(u8.numel() + 8, dtype=torch.uint8, device=DEV)
+        vin = raw_in[off:off + u8.numel()].view(B, H, W, 3)
+        vin.copy_(u8)
+        raw_out = torch.zeros(B * H * W + 8, dtype=torch.uint8, device=DEV)
+        vout = raw_out[off:off + B * H * W].view(B, H, W)
+        assert vin.data_ptr() % 4 != 0 or off % 4 == 0
+        raw_lg = torch.zeros(ref_lg.numel() + 8, device=DEV)
+        vlg = raw_lg[off:off + ref_lg.numel()].view(lg_shape)          # 4-byte aligned only for odd `off`
+        m.segment(vin, mean, std, out=vout, logits=vlg)
+        assert torch.equal(vout, ref), off
+        # the scalar fall-back kernels sum in a different order than the vectorised ones: fp32 rounding differences only
+        assert (vlg - ref_lg).abs().max().item() <= 1e-4, off
+        assert float(raw_lg[:off].abs().sum()) == 0 and float(raw_lg[off + ref_lg.numel():].abs().sum()) == 0
+        assert int(raw_out[:off].sum()) == 0 and int(raw_out[off + B * H * W:].sum()) == 0    # nothing written outside the view
