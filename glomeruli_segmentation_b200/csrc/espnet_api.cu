@@ -968,6 +968,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     if (h->net == ESPNET_NET_ENCODER && a->prob_acc) return fail(h, ESPNET_EINVAL, "espnet_forward: prob_acc needs the full net");
     const Workspace L = layout(h, a->B, a->H, a->W);
     if (a->workspace_bytes < L.total * sizeof(float)) return fail(h, ESPNET_ESTATE, "espnet_forward: workspace too small");
+    if (((uintptr_t)a->workspace & 255) != 0) return fail(h, ESPNET_EINVAL, "espnet_forward: workspace must be 256-byte aligned (TMA tensor maps, 16 B vector accesses)");
     if ((size_t)a->H * a->W > ((size_t)1 << 30)) return fail(h, ESPNET_ESHAPE, "espnet_forward: crop too large for 32-bit plane offsets");
     if (h->mode == ESPNET_MODE_F16TC && (size_t)a->H * a->W > ((size_t)1 << 27))
         return fail(h, ESPNET_ESHAPE, "espnet_forward: crop too large for the tensor-core path's 32-bit channel offsets");

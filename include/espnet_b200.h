@@ -77,7 +77,7 @@ typedef struct {
     int prob_init;        /* 1: overwrite prob_acc instead of adding (first fold)                            */
     int mask_from_prob;   /* 1: mask = argmax(prob_acc after this call's add) instead of argmax(logits)      */
     /* ---- scratch ---- */
-    void* workspace;      /* device, >= espnet_workspace_bytes(...)                                         */
+    void* workspace;      /* device, >= espnet_workspace_bytes(...), 256-byte aligned (cudaMalloc / torch are) */
     size_t workspace_bytes;
     void* stream;         /* cudaStream_t                                                                   */
 } espnet_forward_args;
