@@ -970,8 +970,11 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     if (a->workspace_bytes < L.total * sizeof(float)) return fail(h, ESPNET_ESTATE, "espnet_forward: workspace too small");
     if (((uintptr_t)a->workspace & 255) != 0) return fail(h, ESPNET_EINVAL, "espnet_forward: workspace must be 256-byte aligned (TMA tensor maps, 16 B vector accesses)");
     if ((size_t)a->H * a->W > ((size_t)1 << 30)) return fail(h, ESPNET_ESHAPE, "espnet_forward: crop too large for 32-bit plane offsets");
-    if (h->mode == ESPNET_MODE_F16TC && (size_t)a->H * a->W > ((size_t)1 << 27))
-        return fail(h, ESPNET_ESHAPE, "espnet_forward: crop too large for the tensor-core path's 32-bit channel offsets");
+    // tensor-core kernels address channel planes as 32-bit byte offsets inside one crop; the tightest one is the level-3
+    // 3x3-s2 reduce loader: 144 channels x (H/4 x W/4) x 4 B < 2^32  ->  H*W < 1.19e8; 2^26 (8192 x 8192) keeps a margin
+    if ((h->mode == ESPNET_MODE_F16TC || h->fp32_impl != 0) && (size_t)a->H * a->W > ((size_t)1 << 26))
+        return fail(h, ESPNET_ESHAPE, "espnet_forward: crop larger than 2^26 pixels: the tensor-core kernels use 32-bit channel offsets "
+                                      "(use set_option(\"fp32_impl\", 0) or tile the crop)");
 
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)a->stream;

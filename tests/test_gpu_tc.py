@@ -196,3 +196,22 @@ def test_random_shapes_all_paths_agree(fold_sd):
         m_tc.set_option("tc_pair", 1).segment(u8, mean, std, logits=l2)
         assert (l1 - l0).abs().max().item() <= LOGIT_TOL, (B, H, W)
         assert torch.equal(l1, l2), (B, H, W)
+
+
+def test_large_crop_paths_agree(fold_sd):
+    """One 2048 x 2048 crop (256 x 256 level-3 map, 32 768 MMA tiles at level 2): split tensor-core path vs the CUDA-core
+    fp32 path within the fp32 bar, pair kernels bit-equal, f16tc masks within the agreement bar of the fp32 masks."""
+    sd = fold_sd(1)
+    mean, std = FOLD_MEAN_STD[1]
+    B, H, W = 1, 2048, 2048
+    u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=99, sigma=3.0)).to(DEV)
+    l0, l1, l2 = (torch.empty((B, 5, H, W), device=DEV) for _ in range(3))
+    m0 = _model(sd, "fp32").set_option("fp32_impl", 0).segment(u8, mean, std, logits=l0)
+    m_tc = _model_split(sd)
+    m1 = m_tc.set_option("tc_pair", 0).segment(u8, mean, std, logits=l1).clone()
+    m_tc.set_option("tc_pair", 1).segment(u8, mean, std, logits=l2)
+    assert (l1 - l0).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(l1, l2)
+    assert (m1 == m0).float().mean().item() >= 0.9999
+    mh = _model(sd, "f16tc").segment(u8, mean, std)
+    assert (mh == m0).float().mean().item() >= AGREE
