@@ -215,3 +215,20 @@ def test_large_crop_paths_agree(fold_sd):
     assert (m1 == m0).float().mean().item() >= 0.9999
     mh = _model(sd, "f16tc").segment(u8, mean, std)
     assert (mh == m0).float().mean().item() >= AGREE
+
+
+@pytest.mark.parametrize("opt,val", [("tc_reduce", 0), ("l2_reverse", 0), ("dec_impl", 0)])
+def test_kernel_variant_options_keep_the_bars(fold_sd, opt, val):
+    """Every selectable kernel variant (CUDA-core reduce feeding the tensor-core branches, forward tile walk in the 1x1
+    reduce, one-pixel decoder kernels) stays inside the fp32 bar in split mode and the agreement bar in f16tc mode."""
+    sd = fold_sd(3)
+    mean, std = FOLD_MEAN_STD[3]
+    B, H, W = 2, 264, 328
+    u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=123, sigma=3.0)).to(DEV)
+    ref = torch.empty((B, 5, H, W), device=DEV)
+    mref = _model(sd, "fp32").set_option("fp32_impl", 0).segment(u8, mean, std, logits=ref)
+    lg = torch.empty_like(ref)
+    _model_split(sd).set_option(opt, val).segment(u8, mean, std, logits=lg)
+    assert (lg - ref).abs().max().item() <= LOGIT_TOL
+    mh = _model(sd, "f16tc").set_option(opt, val).segment(u8, mean, std)
+    assert (mh == mref).float().mean().item() >= AGREE
