@@ -1355,6 +1355,19 @@ int espnet_preprocess_resize(const uint8_t* crops, int B, int h, int w, const fl
     return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
 }
 
+int espnet_preprocess_resize_boxes(const uint8_t* slide, int slide_h, int slide_w, const int32_t* boxes_dev, int B, const float mean[3],
+                                   const float std_[3], const int32_t* xs_dev, const float* xf_dev, const int32_t* ys_dev, const float* yf_dev,
+                                   float* out, int H, int W, void* stream) {
+    if (!slide || !boxes_dev || !mean || !std_ || !xs_dev || !xf_dev || !ys_dev || !yf_dev || !out || B <= 0 || slide_h <= 0 || slide_w <= 0 ||
+        H <= 0 || W <= 0 || B > 65535)
+        return ESPNET_EINVAL;
+    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    preprocess_resize_boxes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(slide, slide_h, slide_w, boxes_dev, mean[0], mean[1], mean[2], std_[0],
+                                                                          std_[1], std_[2], xs_dev, xf_dev, ys_dev, yf_dev, out, H, W);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
 int espnet_resize_nearest_u8(const uint8_t* src, int B, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* ysrc_dev,
                              const int32_t* xsrc_dev, void* stream) {
     if (!src || !dst || !ysrc_dev || !xsrc_dev || B <= 0 || sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0 || B > 65535 || dh > 65535) return ESPNET_EINVAL;

@@ -44,6 +44,41 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const unsigned c
     }
 }
 
+// Box -> crop extraction fused with the same front-end (make_seg_data.py:347-361 output_org_files + VisualizeResults_iou.py:103-119):
+// crop b is the level-0 region boxes[b] = (x0, y0, x1, y1) of the resident BGR slide (pixels outside the slide are 0, what
+// OpenSlide's read_region pads and cv2.imread's alpha drop leave), resized to W x H.  Boxes differ in size, so every box has
+// its own LUT row: xs/xf are [B][W], ys/yf are [B][H] (host-computed, OpenCV's index arithmetic).
+__global__ void __launch_bounds__(256) preprocess_resize_boxes_kernel(const unsigned char* __restrict__ slide, int SH, int SW,
+                                                                      const int32_t* __restrict__ boxes,
+                                                                      float m0, float m1, float m2, float s0, float s1, float s2,
+                                                                      const int32_t* __restrict__ xs, const float* __restrict__ xf,
+                                                                      const int32_t* __restrict__ ys, const float* __restrict__ yf,
+                                                                      float* __restrict__ out, int H, int W) {
+    const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (dx >= W || dy >= H) return;
+    const int bx0 = boxes[4 * b], by0 = boxes[4 * b + 1];
+    const int w = boxes[4 * b + 2] - bx0, h = boxes[4 * b + 3] - by0;
+    const int x0 = xs[(size_t)b * W + dx], y0 = ys[(size_t)b * H + dy];
+    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+    const float fx = xf[(size_t)b * W + dx], fy = yf[(size_t)b * H + dy];
+    const float ax = __fsub_rn(1.f, fx), ay = __fsub_rn(1.f, fy);
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        auto S = [&](int y, int x) {
+            const int gy = by0 + y, gx = bx0 + x;
+            const float p = (gy >= 0 && gy < SH && gx >= 0 && gx < SW) ? (float)slide[((size_t)gy * SW + gx) * 3 + c] : 0.f;
+            return __fdiv_rn(__fsub_rn(p, mean[c]), stdv[c]);
+        };
+        const float r0 = __fadd_rn(__fmul_rn(S(y0, x0), ax), __fmul_rn(S(y0, x1), fx));
+        const float r1 = __fadd_rn(__fmul_rn(S(y1, x0), ax), __fmul_rn(S(y1, x1), fx));
+        const float v = __fadd_rn(__fmul_rn(r0, ay), __fmul_rn(r1, fy));
+        out[((size_t)(b * 3 + c) * H + dy) * W + dx] = __fdiv_rn(v, 255.f);
+    }
+}
+
 // dst[b][y][x] = src[b][ysrc[y]][xsrc[x]]  (cv2 INTER_NEAREST source indices from the host)
 __global__ void __launch_bounds__(256) resize_nearest_u8_kernel(const unsigned char* __restrict__ src, int B, int sh, int sw,
                                                                 unsigned char* __restrict__ dst, int dh, int dw,

@@ -64,6 +64,48 @@ def preprocess_resize(crops_u8: torch.Tensor, mean: Sequence[float], std: Sequen
     return out
 
 
+def crop_regions(boxes: Sequence[Sequence[float]]):
+    """make_seg_data.py:347-361: per detected box the level-0 read_region arguments (x, y, w, h) and the crop's file
+    stem `xmin{}_ymin{}_xmax{}_ymax{}` in /8 coordinates (:359) -- the name overlay() later searches for
+    (eval_wsi_segmentation.py:272)."""
+    regions = [(b[0], b[1], b[2] - b[0], b[3] - b[1]) for b in boxes]
+    names = ["xmin{}_ymin{}_xmax{}_ymax{}".format(int(b[0] / 8), int(b[1] / 8), int(b[2] / 8), int(b[3] / 8)) for b in boxes]
+    return regions, names
+
+
+def preprocess_boxes(slide_u8: torch.Tensor, boxes: Sequence[Sequence[float]], mean: Sequence[float], std: Sequence[float],
+                     width: int = 1024, height: int = 512) -> torch.Tensor:
+    """Box -> crop -> network input in one kernel: what make_seg_data.output_org_files (:347-361) cuts out of the slide and
+    VisualizeResults_iou.py:103-119 then normalises and resizes to inWidth x inHeight (defaults 1024 x 512, :297-298).
+    slide_u8: resident CUDA uint8 [SH,SW,3] in BGR (cv2.imread order); boxes: [[xmin,ymin,xmax,ymax,...]] level-0 px, may
+    overhang the slide (zero padding).  Returns fp32 [B,3,height,width]."""
+    if slide_u8.dtype != torch.uint8 or slide_u8.dim() != 3 or slide_u8.shape[-1] != 3 or not slide_u8.is_cuda or not slide_u8.is_contiguous():
+        raise RuntimeError("preprocess_boxes() wants a contiguous CUDA uint8 [SH,SW,3] BGR slide")
+    ib = np.array([[int(b[0]), int(b[1]), int(b[2]), int(b[3])] for b in boxes], np.int32).reshape(-1, 4)
+    if len(ib) == 0 or (ib[:, 2] <= ib[:, 0]).any() or (ib[:, 3] <= ib[:, 1]).any():
+        raise RuntimeError("preprocess_boxes() needs at least one box and positive box sizes")
+    B = len(ib)
+    dev = slide_u8.device
+    xs, xf = np.empty((B, width), np.int32), np.empty((B, width), np.float32)
+    ys, yf = np.empty((B, height), np.int32), np.empty((B, height), np.float32)
+    cache = {}
+    for i, (x0, y0, x1, y1) in enumerate(ib):
+        for n, dst, (ia, fa) in ((int(x1 - x0), width, (xs, xf)), (int(y1 - y0), height, (ys, yf))):
+            if (n, dst) not in cache:
+                cache[(n, dst)] = bilinear_lut(n, dst)
+            ia[i], fa[i] = cache[(n, dst)]
+    d = [torch.from_numpy(a).to(dev) for a in (ib, xs, xf, ys, yf)]
+    out = torch.empty((B, 3, height, width), dtype=torch.float32, device=dev)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(dev):
+        rc = _lib.lib().espnet_preprocess_resize_boxes(slide_u8.data_ptr(), int(slide_u8.shape[0]), int(slide_u8.shape[1]), d[0].data_ptr(), B, m, s,
+                                                       d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(), out.data_ptr(),
+                                                       height, width, _stream(dev))
+    _lib.check(rc, None, "espnet_preprocess_resize_boxes")
+    return out
+
+
 def resize_mask_nearest(masks: torch.Tensor, height: int, width: int) -> torch.Tensor:
     """CUDA uint8 [B,H,W] -> [B,height,width] with cv2 INTER_NEAREST indices (:129)."""
     if masks.dtype != torch.uint8 or masks.dim() != 3 or not masks.is_cuda:

@@ -59,6 +59,17 @@ def tile_grid(slide_w: int, slide_h: int, std_size: float = 512, mpp_x: float = 
     )
 
 
+def select_level(objective_power: float, level_downsamples: Sequence[float]) -> Tuple[int, float]:
+    """detect_glomus_test.py:255-262: the first pyramid level at <= 5x magnification; when none qualifies the reference keeps
+    its defaults target_level = 3, slide_downsample = 8.0."""
+    target_level, downsample = 3, 8.0
+    for level, ds in enumerate(level_downsamples):
+        if objective_power / ds <= 5.0:
+            target_level, downsample = level, level_downsamples[level]
+            break
+    return target_level, downsample
+
+
 def stitch_y_limit(slide_w: int, slide_h: int, ws: int) -> int:
     """Rows >= this value are never written by the reference's window loop: windows whose ymax exceeds the
     slide WIDTH are skipped (`if ymax > slide_width: continue`, eval_wsi_segmentation.py:194, sic)."""

@@ -160,6 +160,12 @@ ESPNET_API int espnet_nearest_lut(int src_len, int dst_len, int32_t* idx_host);
 ESPNET_API int espnet_preprocess_resize(const uint8_t* crops, int B, int h, int w, const float mean[3], const float std_[3],
                                         const int32_t* xs_dev, const float* xf_dev, const int32_t* ys_dev, const float* yf_dev,
                                         float* out, int H, int W, void* stream);
+/* make_seg_data.py:347-361 (output_org_files: level-0 read_region of every detected box) fused with the front-end above: crop b is
+ * boxes_dev[b] = (x0,y0,x1,y1) int32 of the resident BGR u8 slide [slide_h][slide_w][3] (outside pixels are 0 like OpenSlide pads),
+ * resized to W x H.  Box sizes differ, so the LUTs are per box: xs/xf [B][W] from espnet_bilinear_lut(x1-x0, W), ys/yf [B][H]. */
+ESPNET_API int espnet_preprocess_resize_boxes(const uint8_t* slide, int slide_h, int slide_w, const int32_t* boxes_dev, int B,
+                                              const float mean[3], const float std_[3], const int32_t* xs_dev, const float* xf_dev,
+                                              const int32_t* ys_dev, const float* yf_dev, float* out, int H, int W, void* stream);
 /* VisualizeResults_iou.py:129: class maps [B,sh,sw] -> [B,dh,dw], cv2 INTER_NEAREST (LUTs from espnet_nearest_lut). */
 ESPNET_API int espnet_resize_nearest_u8(const uint8_t* src, int B, int sh, int sw, uint8_t* dst, int dh, int dw,
                                         const int32_t* ysrc_dev, const int32_t* xsrc_dev, void* stream);

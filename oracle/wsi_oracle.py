@@ -2,10 +2,17 @@
 
 numpy / pure-Python restatement of the integer work either side of the ESPNet forward:
 the overlapping tiler (T1), the stitch windows (T2), the box paste + max merge (T3), the /8
-nearest down-sample + paste (T4) and the confusion-matrix IoU.  The reference scripts that hold
-these cannot be imported here (they need tensorflow / openslide / labelme at import time,
-SURVEY.md 8(c)), so each function follows the cited line range and reproduces Python `int()`,
-`//` and `math.ceil` on floats exactly.  Only tests / smoke / bench's CPU legs may import this.
+nearest down-sample + paste (T4), the box -> crop extraction and the confusion-matrix IoU.
+Each function follows the cited line range and reproduces Python `int()`, `//` and `math.ceil`
+on floats exactly.
+
+PINNED AGAINST THE REFERENCE ITSELF: tests/golden/make_wsi_golden.py imports the unmodified
+reference scripts (tensorflow / openslide / labelme replaced by stub modules, an in-memory slide
+behind openslide.open_slide) and runs the real GlomusDetector.scan_region,
+Generate_Segmentation_Gt.generate_pred_wsi / overlay / generate_whole_img,
+AnnotationHandler.check_overlap and make_seg_data's output_org_files on seeded slides
+(tests/wsi_cases.py); tests/test_reference_golden_cpu.py holds this module equal to those
+fixtures (tests/golden/wsi_golden.npz).  Only tests / smoke / bench's CPU legs may import this.
 """
 from __future__ import annotations
 
@@ -44,16 +51,41 @@ def tile_grid(slide_w: int, slide_h: int, std_size: float, mpp_x: float, mpp_y: 
     return origins, n_x, n_y, win_x, win_y, stride_x, stride_y
 
 
+def select_level(objective_power: float, level_downsamples: Sequence[float]):
+    """detect_glomus_test.py:255-262: the first pyramid level whose magnification is <= 5x; when none
+    is, the reference keeps its defaults `target_level = 3`, `slide_downsample = 8.0` (sic).
+    Returns (target_level, slide_downsample)."""
+    downsample, target_level = 8.0, 3                                     # :255-256
+    for level, ds in enumerate(level_downsamples):                        # :257
+        if objective_power / ds <= 5.0:                                   # :258
+            target_level = level
+            downsample = level_downsamples[level]
+            break
+    return target_level, downsample
+
+
 def read_tile(slide: np.ndarray, x0: int, y0: int, win_x: int, win_y: int) -> np.ndarray:
     """`slide.read_region((x0,y0), level 0, (win_x, win_y))` on an in-memory [H,W,3] slide:
     out-of-bounds pixels are zero (openslide pads with transparent black; the alpha channel is
     dropped at detect_glomus_test.py:276)."""
     h, w = slide.shape[:2]
     out = np.zeros((win_y, win_x, slide.shape[2]), slide.dtype)
+    cx0, cy0 = max(x0, 0), max(y0, 0)
     x1, y1 = min(x0 + win_x, w), min(y0 + win_y, h)
-    if x1 > x0 and y1 > y0:
-        out[: y1 - y0, : x1 - x0] = slide[y0:y1, x0:x1]
+    if x1 > cx0 and y1 > cy0:
+        out[cy0 - y0: y1 - y0, cx0 - x0: x1 - x0] = slide[cy0:y1, cx0:x1]
     return out
+
+
+def crop_regions(boxes: Sequence[Sequence[float]]):
+    """make_seg_data.py:347-361 (output_org_files): per detected box the level-0 `read_region` arguments
+    (x, y, w, h) and the crop's file stem `xmin{}_ymin{}_xmax{}_ymax{}` in /8 coordinates (:359)."""
+    regions, names = [], []
+    for b in boxes:
+        regions.append((b[0], b[1], b[2] - b[0], b[3] - b[1]))           # :358
+        names.append("xmin{}_ymin{}_xmax{}_ymax{}".format(int(b[0] / MAGNIFICATION), int(b[1] / MAGNIFICATION),
+                                                           int(b[2] / MAGNIFICATION), int(b[3] / MAGNIFICATION)))   # :359
+    return regions, names
 
 
 # ------------------------------------------------------------------------------------------
