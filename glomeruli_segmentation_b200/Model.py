@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib
 
-__all__ = ["ESPNet", "ESPNet_Encoder", "ESPNetEnsemble", "FOLD_MEAN_STD"]
+__all__ = ["ESPNet", "ESPNet_Encoder", "ESPNetEnsemble", "GraphedSegmenter", "FOLD_MEAN_STD"]
 
 # per-fold BGR mean / std published by the reference (README.md:243-249)
 FOLD_MEAN_STD = {
@@ -230,7 +230,12 @@ class _KernelBacked(nn.Module):
         self._mark_dirty()
 
     def set_mode(self, mode: str):
-        """'fp32' (CUDA-core FMA, 1e-3 logit bar) or 'f16tc' (fp16 storage + tcgen05, mask-parity bar)."""
+        """'fp32' (default): fp32-EQUIVALENT arithmetic, logits within 1e-3 of the reference.  With the default option
+        fp32_impl=1 the block contractions run on tcgen05 as 3-term fp16 operand splits (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+        with a scaled by 1/4 and w by 4: 22-bit mantissa products, fp32 accumulate / storage); activations must stay below
+        |a| < 2.6e5 (fp16 range of a/4) -- far above anything a normalised crop produces (|a| < 40 measured) -- beyond it
+        the logits turn inf/NaN; set_option('fp32_impl', 0) selects plain fp32 FMA on CUDA cores (no range limit, ~4x slower).
+        'f16tc': single fp16 operands on tcgen05 (fp32 accumulate / storage), held to the 0.999 mask-agreement bar only."""
         self._engine.mode = {"fp32": _lib.MODE_FP32, "f16tc": _lib.MODE_F16TC}[mode]
         if self._engine.handle is not None:
             _lib.check(_lib.lib().espnet_set_mode(self._engine.handle, self._engine.mode), self._engine.handle, "espnet_set_mode")
@@ -313,13 +318,24 @@ class _KernelBacked(nn.Module):
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Tiles are read straight out of a resident slide [SH,SW,3] u8 at origins[B,2] (x0,y0) int32 -- the
         read_region of detect_glomus_test.py:272 (zero padding outside the slide) fused into the stem."""
+        if slide_u8.dtype != torch.uint8 or slide_u8.dim() != 3 or slide_u8.shape[-1] != 3 or not slide_u8.is_cuda or not slide_u8.is_contiguous():
+            raise RuntimeError("segment_tiles() wants a contiguous CUDA uint8 [SH,SW,3] slide")
+        if origins.dtype != torch.int32 or origins.dim() != 2 or origins.shape[1] != 2 or not origins.is_contiguous() or origins.device != slide_u8.device:
+            raise RuntimeError("origins must be a contiguous int32 [B,2] tensor on the slide's device")
         B = origins.shape[0]
         eng = self._ready(slide_u8.device)
         if out is None:
             out = torch.empty((B, win_h, win_w), dtype=torch.uint8, device=slide_u8.device)
+        elif out.dtype != torch.uint8 or not out.is_contiguous() or out.numel() != B * win_h * win_w or out.device != slide_u8.device:
+            raise RuntimeError("out must be a contiguous uint8 [B,win_h,win_w] tensor on the slide's device")
         eng.forward(slide_u8, _lib.IN_U8_SLIDE, B, win_h, win_w, mean, std, origins=origins,
                     slide_hw=(slide_u8.shape[0], slide_u8.shape[1]), mask=out)
         return out
+
+    def capture(self, B: int, H: int, W: int, mean, std, want_logits: bool = False) -> "GraphedSegmenter":
+        """Record normalise + forward + arg-max for a fixed [B,H,W] into a CUDA graph (espnet_graph_capture): one launch per
+        call instead of ~30 -- the per-crop loop of VisualizeResults_iou.py:100-129 is batch 1 and launch-latency bound."""
+        return GraphedSegmenter(self, B, H, W, mean, std, want_logits)
 
     def host_pipeline(self, B: int, H: int, W: int, mean, std, depth: int = 2) -> "HostPipeline":
         """Pipelined host-to-host segmentation of a stream of batches (see HostPipeline)."""
@@ -337,6 +353,43 @@ class _KernelBacked(nn.Module):
         _lib.check(_lib.lib().espnet_segment_host(eng.handle, crops_u8.ctypes.data, B, H, W, m, s, out.ctypes.data),
                    eng.handle, "espnet_segment_host")
         return out
+
+
+class GraphedSegmenter:
+    """A captured forward with its own static buffers: `run(crops_u8)` copies the crops into the static input (or use
+    `.input` directly), replays the graph on the current stream and returns the static mask tensor `.mask` (and `.logits`)."""
+
+    def __init__(self, model: "_KernelBacked", B: int, H: int, W: int, mean, std, want_logits: bool = False):
+        dev = model._param_device()
+        eng = model._ready(dev)
+        self.model, self.eng = model, eng
+        self.input = torch.zeros((B, H, W, 3), dtype=torch.uint8, device=dev)
+        self.mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        nc = model.classes
+        lshape = (B, nc, H, W) if model._net == _lib.NET_FULL else (B, nc, H // 8, W // 8)
+        self.logits = torch.empty(lshape, dtype=torch.float32, device=dev) if want_logits else None
+        need = _lib.lib().espnet_workspace_bytes(eng.handle, B, H, W)
+        self.ws = torch.empty(need, dtype=torch.uint8, device=dev)          # private: the engine's cached workspace may be re-allocated
+        a = _lib.ForwardArgs()
+        a.x, a.in_fmt, a.B, a.H, a.W = self.input.data_ptr(), _lib.IN_U8_BGR_HWC, B, H, W
+        for i in range(3):
+            a.mean[i], a.std_[i] = float(mean[i]), float(std[i])
+        a.mask = self.mask.data_ptr()
+        a.logits = self.logits.data_ptr() if want_logits else None
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        gid = C.c_int(-1)
+        torch.cuda.synchronize(dev)
+        _lib.check(_lib.lib().espnet_graph_capture(eng.handle, C.byref(a), C.byref(gid)), eng.handle, "espnet_graph_capture")
+        self.graph_id = gid.value
+
+    def run(self, crops_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.model._dirty:
+            raise RuntimeError("the module's weights changed after capture(); capture again")
+        if crops_u8 is not None:
+            self.input.copy_(crops_u8, non_blocking=True)
+        st = torch.cuda.current_stream(self.input.device).cuda_stream
+        _lib.check(_lib.lib().espnet_graph_launch(self.eng.handle, self.graph_id, st), self.eng.handle, "espnet_graph_launch")
+        return self.mask
 
 
 class HostPipeline:

@@ -41,12 +41,17 @@ SYMBOLS = {
     "espnet_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "espnet_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "espnet_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs)]),
+    "espnet_graph_capture": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.POINTER(C.c_int)]),
+    "espnet_graph_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "espnet_graph_destroy": (C.c_int, [C.c_void_p, C.c_int]),
     "espnet_read_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
     "espnet_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "espnet_get_profile": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "espnet_segment_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
     "espnet_stitch_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "espnet_stitch_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
+    "espnet_stitch_grid_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
+    "espnet_max_merge_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "espnet_ds8_lut": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "espnet_downsample_lut": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "espnet_confusion_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -98,6 +99,10 @@ struct espnet_handle {
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof;
+    // captured forwards (espnet_graph_capture): fixed buffers, one cudaGraphLaunch per forward
+    struct GraphRec { cudaGraphExec_t exec = nullptr; };
+    std::vector<GraphRec> graphs;
+    std::set<const void*> smem_done;   // kernels whose dynamic shared-memory limit has been raised on this device
     // host-convenience path (espnet_segment_host)
     cudaStream_t own_stream = nullptr;
     void* hb_in = nullptr; void* hb_mask = nullptr; void* hb_ws = nullptr;
@@ -122,6 +127,21 @@ struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Handle-less entry points launch on the device that OWNS their first device pointer, whatever device is current.
+struct PtrDeviceGuard {
+    int prev = -1;
+    explicit PtrDeviceGuard(const void* p) {
+        cudaPointerAttributes at{};
+        if (p && cudaPointerGetAttributes(&at, p) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+            cudaGetDevice(&prev);
+            if (prev != at.device) cudaSetDevice(at.device); else prev = -1;
+        } else {
+            cudaGetLastError();     // a host / unknown pointer is the callee's problem, not a sticky error
+        }
+    }
+    ~PtrDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 // Brackets one kernel launch with CUDA events on the launching stream when profiling is on.
@@ -456,7 +476,10 @@ Workspace layout(const espnet_t* h, int B, int H, int W) {
 
 template <typename K>
 int set_smem(espnet_t* h, K kernel, size_t bytes) {
+    // once per (handle = device, kernel): the attribute is sticky, and the call costs a microsecond per launch otherwise
+    if (h && h->smem_done.count((const void*)kernel)) return ESPNET_OK;
     CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (h) h->smem_done.insert((const void*)kernel);
     return ESPNET_OK;
 }
 
@@ -862,6 +885,7 @@ void espnet_destroy(espnet_t* h) {
     if (h->hb_mask) cudaFree(h->hb_mask);
     if (h->hb_ws) cudaFree(h->hb_ws);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto& gr : h->graphs) { if (gr.exec) cudaGraphExecDestroy(gr.exec); }
     for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     delete h;
 }
@@ -899,7 +923,7 @@ int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n) {
     const std::string e = h->net == ESPNET_NET_FULL ? "encoder." : "";
     Packer pk;
     pk.sd = &sd;
-    Packed& o = h->pk;
+    Packed o{};                // built locally and swapped in only when everything succeeded: a failed repack leaves the old weights intact
     o.l2.assign(h->p, BlockW());
     o.l3.assign(h->q, BlockW());
     bool ok = true;
@@ -936,6 +960,12 @@ int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n) {
     }
     if (!ok) return fail(h, ESPNET_EMISSING, "espnet_pack_weights: " + (pk.missing.empty() ? std::string("packing failed") : pk.missing));
     DeviceGuard g(h->device);
+    // forwards may still be running on non-blocking streams (HostPipeline, own_stream) with the old blobs: wait for the device
+    // before they are overwritten or freed; from here on a failure leaves the handle unpacked, never half-packed
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->packed = false;
+    for (auto& gr : h->graphs) { if (gr.exec) cudaGraphExecDestroy(gr.exec); }
+    h->graphs.clear();
     if (h->dparams && h->nparams < pk.blob.size()) { cudaFree(h->dparams); h->dparams = nullptr; }
     if (!h->dparams) CUDA_TRY(h, cudaMalloc(&h->dparams, pk.blob.size() * sizeof(float)));
     h->nparams = pk.blob.size();
@@ -945,6 +975,7 @@ int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensors, int n) {
     if (!h->dparams_h) CUDA_TRY(h, cudaMalloc(&h->dparams_h, pk.blob_h.size() * 2));
     h->nparams_h = pk.blob_h.size() * 2;
     CUDA_TRY(h, cudaMemcpy(h->dparams_h, pk.blob_h.data(), pk.blob_h.size() * 2, cudaMemcpyHostToDevice));
+    h->pk = o;
     h->packed = true;
     return ESPNET_OK;
 }
@@ -1097,6 +1128,49 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
     return run_tail<20>(h, a, L, ws, st);
 }
 
+// One forward with FIXED buffers recorded into a CUDA graph: ~30 kernel launches become one cudaGraphLaunch, which is what the
+// reference's per-crop loop (VisualizeResults_iou.py:100-129, batch 1) needs -- at batch 1 the forward is launch-latency bound.
+int espnet_graph_capture(espnet_t* h, const espnet_forward_args* a, int* graph_id) {
+    if (!h || !a || !graph_id) return fail(h, ESPNET_EINVAL, "espnet_graph_capture: NULL argument");
+    if (h->profiling) return fail(h, ESPNET_ESTATE, "espnet_graph_capture: switch profiling off first (events cannot be captured per kernel)");
+    DeviceGuard g(h->device);
+    espnet_forward_args b = *a;
+    b.stream = h->own_stream;
+    // an uncaptured pass first: raises the shared-memory limits (cudaFuncSetAttribute) and validates the arguments outside the capture
+    int rc = espnet_forward(h, &b);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->own_stream));
+    CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeRelaxed));
+    rc = espnet_forward(h, &b);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->own_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || !graph) return fail(h, ESPNET_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    espnet_handle::GraphRec rec;
+    e = cudaGraphInstantiate(&rec.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(h, ESPNET_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    h->graphs.push_back(rec);
+    *graph_id = (int)h->graphs.size() - 1;
+    return ESPNET_OK;
+}
+
+int espnet_graph_launch(espnet_t* h, int graph_id, void* stream) {
+    if (!h || graph_id < 0 || graph_id >= (int)h->graphs.size() || !h->graphs[graph_id].exec)
+        return fail(h, ESPNET_EINVAL, "espnet_graph_launch: unknown graph (a repack of the weights drops all captured graphs)");
+    DeviceGuard g(h->device);
+    CUDA_TRY(h, cudaGraphLaunch(h->graphs[graph_id].exec, (cudaStream_t)stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return ESPNET_OK;
+}
+
+int espnet_graph_destroy(espnet_t* h, int graph_id) {
+    if (!h || graph_id < 0 || graph_id >= (int)h->graphs.size()) return ESPNET_EINVAL;
+    DeviceGuard g(h->device);
+    if (h->graphs[graph_id].exec) { cudaGraphExecDestroy(h->graphs[graph_id].exec); h->graphs[graph_id].exec = nullptr; }
+    return ESPNET_OK;
+}
+
 // Hardware self-test of the tcgen05 operand convention (kernels_tc.cuh: tc_selftest_kernel): random fp16 A / B,
 // one tap shifted by (dy, dx), compared with a double-precision host reference.  Returns the max abs error.
 int espnet_tc_selftest(int device, int nkc, int nout, int dy, int dx, int use_tma, float* max_abs_err) {
@@ -1244,6 +1318,7 @@ int espnet_segment_host(espnet_t* h, const uint8_t* crops_host, int B, int H, in
 // ---------------------------------------------------------------------------------- stitching
 int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit, const int32_t* boxes,
                         const int64_t* mask_offsets, const uint8_t* masks, int n_boxes, void* stream) {
+    PtrDeviceGuard _dg(slide_mask);
     if (!slide_mask || !boxes || !mask_offsets || !masks || slide_h <= 0 || slide_w <= 0 || n_boxes < 0) return ESPNET_EINVAL;
     if (((uintptr_t)slide_mask & 3) != 0) return ESPNET_EINVAL;   // 32-bit merge words
     if (n_boxes == 0) return ESPNET_OK;
@@ -1254,23 +1329,52 @@ int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_lim
     return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
 }
 
-int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks, int n_x, int n_y,
-                       int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream) {
-    if (!slide_mask || !tile_masks || slide_h <= 0 || slide_w <= 0 || n_x <= 0 || n_y <= 0 || win_x <= 0 || win_y <= 0 ||
-        stride_x <= 0 || stride_y <= 0 || tile_row0 < 0 || tile_rows < 0 || tile_row0 + tile_rows > n_y)
+static int stitch_grid_launch(uint8_t* out, int out_y0, int out_rows, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks, int n_x,
+                              int n_y, int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream) {
+    PtrDeviceGuard _dg(out);
+    if (!out || !tile_masks || slide_h <= 0 || slide_w <= 0 || n_x <= 0 || n_y <= 0 || win_x <= 0 || win_y <= 0 || stride_x <= 0 ||
+        stride_y <= 0 || tile_row0 < 0 || tile_rows < 0 || tile_row0 + tile_rows > n_y || out_y0 < 0 || out_rows < 0)
         return ESPNET_EINVAL;
-    if (tile_rows == 0) return ESPNET_OK;
-    const long long ylo = (long long)tile_row0 * stride_y;
+    if (tile_rows == 0 || out_rows == 0) return ESPNET_OK;
+    long long ylo = (long long)tile_row0 * stride_y;
     long long yhi = (long long)(tile_row0 + tile_rows - 1) * stride_y + win_y;
     if (yhi > slide_h) yhi = slide_h;
     if (yhi > y_limit) yhi = y_limit;
+    if (ylo < out_y0) ylo = out_y0;
+    if (yhi > (long long)out_y0 + out_rows) yhi = (long long)out_y0 + out_rows;
     if (yhi <= ylo) return ESPNET_OK;
     int gx = (slide_w + 255) / 256;
     if (gx > 64) gx = 64;
-    dim3 grid(gx, (unsigned)(yhi - ylo));
-    if (grid.y > 65535) return ESPNET_ESHAPE;
-    stitch_grid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(slide_mask, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x, win_y,
-                                                              stride_x, stride_y, tile_row0, tile_rows);
+    long long gy = yhi - ylo;
+    if (gy > 16384) gy = 16384;          // the kernel strides over the rows: no 65535-row limit on the slide
+    dim3 grid(gx, (unsigned)gy);
+    stitch_grid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, out_y0, out_rows, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x,
+                                                              win_y, stride_x, stride_y, tile_row0, tile_rows);
+    LAUNCH_COUNT();
+    return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+}
+
+int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks, int n_x, int n_y,
+                       int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream) {
+    return stitch_grid_launch(slide_mask, 0, slide_h, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x, win_y, stride_x, stride_y,
+                              tile_row0, tile_rows, stream);
+}
+
+int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks,
+                            int n_x, int n_y, int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream) {
+    if (band_y0 + (long long)band_rows > slide_h) return ESPNET_EINVAL;
+    return stitch_grid_launch(band_mask, band_y0, band_rows, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x, win_y, stride_x,
+                              stride_y, tile_row0, tile_rows, stream);
+}
+
+int espnet_max_merge_u8(uint8_t* dst, const uint8_t* src, size_t n, void* stream) {
+    PtrDeviceGuard _dg(dst);
+    if (!dst || !src) return ESPNET_EINVAL;
+    if (n == 0) return ESPNET_OK;
+    size_t g = (n / 16 + 255) / 256;
+    if (g > 1184) g = 1184;
+    if (g < 1) g = 1;
+    max_merge_u8_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
     LAUNCH_COUNT();
     return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
 }
@@ -1305,6 +1409,7 @@ int espnet_ds8_lut(int slide_len, int ws, int limit, int32_t* lut, int lut_len) 
 
 int espnet_downsample_lut(const uint8_t* level0, int slide_h, int slide_w, uint8_t* ds, int ds_h, int ds_w, const int32_t* ysrc_dev,
                           const int32_t* xsrc_dev, void* stream) {
+    PtrDeviceGuard _dg(level0);
     if (!level0 || !ds || !ysrc_dev || !xsrc_dev || slide_h <= 0 || slide_w <= 0 || ds_h <= 0 || ds_w <= 0) return ESPNET_EINVAL;
     if (ds_h > 65535) return ESPNET_ESHAPE;
     int gx = (ds_w + 255) / 256;
@@ -1346,6 +1451,7 @@ int espnet_nearest_lut(int src_len, int dst_len, int32_t* idx) {
 
 int espnet_preprocess_resize(const uint8_t* crops, int B, int h, int w, const float mean[3], const float std_[3], const int32_t* xs_dev,
                              const float* xf_dev, const int32_t* ys_dev, const float* yf_dev, float* out, int H, int W, void* stream) {
+    PtrDeviceGuard _dg(crops);
     if (!crops || !mean || !std_ || !xs_dev || !xf_dev || !ys_dev || !yf_dev || !out || B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535)
         return ESPNET_EINVAL;
     dim3 grid((W + 31) / 32, (H + 7) / 8, B);
@@ -1358,6 +1464,7 @@ int espnet_preprocess_resize(const uint8_t* crops, int B, int h, int w, const fl
 int espnet_preprocess_resize_boxes(const uint8_t* slide, int slide_h, int slide_w, const int32_t* boxes_dev, int B, const float mean[3],
                                    const float std_[3], const int32_t* xs_dev, const float* xf_dev, const int32_t* ys_dev, const float* yf_dev,
                                    float* out, int H, int W, void* stream) {
+    PtrDeviceGuard _dg(slide);
     if (!slide || !boxes_dev || !mean || !std_ || !xs_dev || !xf_dev || !ys_dev || !yf_dev || !out || B <= 0 || slide_h <= 0 || slide_w <= 0 ||
         H <= 0 || W <= 0 || B > 65535)
         return ESPNET_EINVAL;
@@ -1370,6 +1477,7 @@ int espnet_preprocess_resize_boxes(const uint8_t* slide, int slide_h, int slide_
 
 int espnet_resize_nearest_u8(const uint8_t* src, int B, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* ysrc_dev,
                              const int32_t* xsrc_dev, void* stream) {
+    PtrDeviceGuard _dg(src);
     if (!src || !dst || !ysrc_dev || !xsrc_dev || B <= 0 || sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0 || B > 65535 || dh > 65535) return ESPNET_EINVAL;
     int gx = (dw + 255) / 256;
     if (gx > 64) gx = 64;
@@ -1381,6 +1489,7 @@ int espnet_resize_nearest_u8(const uint8_t* src, int B, int sh, int sw, uint8_t*
 
 int espnet_palette_overlay(const uint8_t* img, const uint8_t* label, size_t npix, const uint8_t* palette_dev, int n_pal, uint8_t* color_out,
                            uint8_t* overlay_out, void* stream) {
+    PtrDeviceGuard _dg(label);
     if (!label || !palette_dev || n_pal <= 0 || n_pal > 256 || (!color_out && !overlay_out) || (overlay_out && !img)) return ESPNET_EINVAL;
     if (npix == 0) return ESPNET_OK;
     size_t g = (npix + 256 * 8 - 1) / (256 * 8);
@@ -1392,6 +1501,7 @@ int espnet_palette_overlay(const uint8_t* img, const uint8_t* label, size_t npix
 
 int espnet_render_ds8(const uint8_t* slide, const uint8_t* label, int slide_h, int slide_w, const uint8_t* palette_dev, int n_pal, uint8_t* out,
                       int ds_h, int ds_w, const int32_t* ysrc_dev, const int32_t* xsrc_dev, void* stream) {
+    PtrDeviceGuard _dg(slide);
     if (!slide || !label || !palette_dev || !out || !ysrc_dev || !xsrc_dev || slide_h <= 0 || slide_w <= 0 || ds_h <= 0 || ds_w <= 0 || n_pal <= 0 ||
         n_pal > 256 || ds_h > 65535)
         return ESPNET_EINVAL;
@@ -1404,6 +1514,7 @@ int espnet_render_ds8(const uint8_t* slide, const uint8_t* label, int slide_h, i
 }
 
 int espnet_class_counts(const uint8_t* maps, int B, size_t pix_per_map, int n_classes, unsigned long long* counts_dev, void* stream) {
+    PtrDeviceGuard _dg(maps);
     if (!maps || !counts_dev || B <= 0 || B > 65535 || n_classes <= 0 || n_classes > 32) return ESPNET_EINVAL;
     if (pix_per_map == 0) return ESPNET_OK;
     size_t g = (pix_per_map + 256 * 64 - 1) / (256 * 64);
@@ -1416,6 +1527,7 @@ int espnet_class_counts(const uint8_t* maps, int B, size_t pix_per_map, int n_cl
 }
 
 int espnet_confusion_hist(const uint8_t* pred, const uint8_t* gt, size_t count, int n_classes, unsigned long long* hist_dev, void* stream) {
+    PtrDeviceGuard _dg(pred);
     if (!pred || !gt || !hist_dev || n_classes <= 0 || n_classes > 32) return ESPNET_EINVAL;
     if (count == 0) return ESPNET_OK;
     size_t g = (count + 256 * 64 - 1) / (256 * 64);

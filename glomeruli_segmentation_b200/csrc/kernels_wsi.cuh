@@ -52,39 +52,56 @@ __global__ void __launch_bounds__(256) stitch_boxes_kernel(unsigned char* __rest
 // T3, gather form for the regular T1 grid (detect_glomus_test.py:268-271): tile k = j*n_x + i sits at
 // (i*stride_x, j*stride_y); each thread owns one slide pixel and takes the max over the (at most
 // ceil(win/stride)^2) tiles that cover it.  Only tile rows [row0,row0+rows) are resident (multi-GPU
-// band sharding); pixels no resident tile covers are left untouched.
-__global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restrict__ slide, int SH, int SW, int y_limit,
+// band sharding); pixels no resident tile covers are left untouched.  The output buffer holds slide rows
+// [out_y0, out_y0 + out_rows) (a rank's band, or the whole slide with out_y0 = 0); grid.y strides over the rows,
+// so slides taller than 65535 px need no special casing.
+__global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restrict__ out, int out_y0, int out_rows, int SH, int SW, int y_limit,
                                                           const unsigned char* __restrict__ tiles, int n_x, int n_y,
                                                           int win_x, int win_y, int sx, int sy, int row0, int rows) {
-    const int ylo = row0 * sy;
-    const int yhi = min(min((row0 + rows - 1) * sy + win_y, SH), y_limit);
-    const int y = ylo + blockIdx.y;
-    if (y >= yhi) return;
-    const int j_hi = min(min(y / sy, n_y - 1), row0 + rows - 1);
-    int j_lo = (y - win_y + sy) / sy;                 // ceil((y - win_y + 1) / sy) for y-win_y+1 > 0
-    if (y - win_y + 1 <= 0) j_lo = 0;
-    j_lo = max(j_lo, row0);
+    const int ylo = max(row0 * sy, out_y0);
+    const int yhi = min(min(min((row0 + rows - 1) * sy + win_y, SH), y_limit), out_y0 + out_rows);
     const size_t tile_sz = (size_t)win_x * win_y;
-    for (int x = blockIdx.x * 256 + threadIdx.x; x < SW; x += gridDim.x * 256) {
-        const int i_hi = min(x / sx, n_x - 1);
-        int i_lo = (x - win_x + sx) / sx;
-        if (x - win_x + 1 <= 0) i_lo = 0;
-        int best = -1;
-        for (int j = j_lo; j <= j_hi; ++j) {
-            const int ty = y - j * sy;
-            if (ty < 0 || ty >= win_y) continue;
-            for (int i = i_lo; i <= i_hi; ++i) {
-                const int tx = x - i * sx;
-                if (tx < 0 || tx >= win_x) continue;
-                const int v = tiles[((size_t)(j - row0) * n_x + i) * tile_sz + (size_t)ty * win_x + tx];
-                best = max(best, v);
+    for (int y = ylo + blockIdx.y; y < yhi; y += gridDim.y) {
+        const int j_hi = min(min(y / sy, n_y - 1), row0 + rows - 1);
+        int j_lo = (y - win_y + sy) / sy;                 // ceil((y - win_y + 1) / sy) for y-win_y+1 > 0
+        if (y - win_y + 1 <= 0) j_lo = 0;
+        j_lo = max(j_lo, row0);
+        for (int x = blockIdx.x * 256 + threadIdx.x; x < SW; x += gridDim.x * 256) {
+            const int i_hi = min(x / sx, n_x - 1);
+            int i_lo = (x - win_x + sx) / sx;
+            if (x - win_x + 1 <= 0) i_lo = 0;
+            int best = -1;
+            for (int j = j_lo; j <= j_hi; ++j) {
+                const int ty = y - j * sy;
+                if (ty < 0 || ty >= win_y) continue;
+                for (int i = i_lo; i <= i_hi; ++i) {
+                    const int tx = x - i * sx;
+                    if (tx < 0 || tx >= win_x) continue;
+                    const int v = tiles[((size_t)(j - row0) * n_x + i) * tile_sz + (size_t)ty * win_x + tx];
+                    best = max(best, v);
+                }
+            }
+            if (best >= 0) {
+                unsigned char* d = out + (size_t)(y - out_y0) * SW + x;
+                *d = (unsigned char)max((int)*d, best);
             }
         }
-        if (best >= 0) {
-            unsigned char* d = slide + (size_t)y * SW + x;
-            *d = (unsigned char)max((int)*d, best);
-        }
     }
+}
+
+// dst[i] = max(dst[i], src[i]) over n bytes: the merge of the rows two ranks' bands share (tile overlap strip) when the
+// band masks are gathered on rank 0.  16 B vectors where both pointers allow it, bytes otherwise.
+__global__ void __launch_bounds__(256) max_merge_u8_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t n) {
+    const bool vec = (((uintptr_t)dst | (uintptr_t)src) & 15) == 0;
+    const size_t nv = vec ? n / 16 : 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nv; i += (size_t)gridDim.x * 256) {
+        uint4 a = reinterpret_cast<uint4*>(dst)[i];
+        const uint4 b = reinterpret_cast<const uint4*>(src)[i];
+        a.x = __vmaxu4(a.x, b.x); a.y = __vmaxu4(a.y, b.y); a.z = __vmaxu4(a.z, b.z); a.w = __vmaxu4(a.w, b.w);
+        reinterpret_cast<uint4*>(dst)[i] = a;
+    }
+    for (size_t i = nv * 16 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        dst[i] = dst[i] > src[i] ? dst[i] : src[i];
 }
 
 // T4 (eval_wsi_segmentation.py:228,236-240): ds[y][x] = level0[ysrc[y]][xsrc[x]], 0 where a LUT entry < 0.

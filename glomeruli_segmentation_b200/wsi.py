@@ -5,8 +5,10 @@ Host side: the integer geometry of the reference's sliding-window tiler
 (`module/espnet/test/eval_wsi_segmentation.py:180-195, 225-240`), evaluated with the same Python
 float / int semantics so the indices are bit-exact.  Device side: tiles are read straight out of the
 resident slide by the stem kernel, and the class maps are merged by the scatter / gather stitch kernels
-of libespnet_b200.so.  Tile rows shard across ranks with no collective in the forward; the only
-exchange is the final max-reduce of the slide masks to rank 0.
+of libespnet_b200.so.  Tile rows shard across ranks with no collective in the forward; every rank holds and
+stitches only its own BAND of slide rows, and the only exchange is the final gather of the band masks on rank 0
+(point-to-point, placed straight into the slide mask; only the rows two bands share -- the tile overlap -- go
+through an element-wise max).
 """
 from __future__ import annotations
 
@@ -89,41 +91,82 @@ def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
     return row0, base + (1 if rank < rem else 0)
 
 
+def band_rows(grid: TileGrid, slide_h: int, rank: int, world: int) -> Tuple[int, int, int, int]:
+    """(tile_row0, tile_rows, y0, y1): the tile rows of `rank` and the slide rows [y0, y1) their tiles cover
+    (clipped to the slide).  Adjacent bands share win_y - stride_y rows (the tile overlap)."""
+    row0, rows = shard_rows(grid.n_y, rank, world)
+    if rows == 0:
+        return row0, 0, 0, 0
+    y0 = row0 * grid.stride_y
+    y1 = min(slide_h, (row0 + rows - 1) * grid.stride_y + grid.win_y)
+    return row0, rows, min(y0, slide_h), max(y1, min(y0, slide_h))
+
+
 def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _check_u8(t: torch.Tensor, what: str, ndim: int, dev=None):
+    if not isinstance(t, torch.Tensor) or t.dtype != torch.uint8 or t.dim() != ndim or not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError("%s must be a contiguous CUDA uint8 tensor with %d dimensions" % (what, ndim))
+    if dev is not None and t.device != dev:
+        raise RuntimeError("%s lives on %s, expected %s" % (what, t.device, dev))
 
 
 def stitch_boxes(slide_mask: torch.Tensor, boxes: Sequence[Sequence[float]], masks: Sequence[torch.Tensor], ws: int = 2400):
     """T3 for arbitrary boxes (eval_wsi_segmentation.py:259-316): every class map is max-merged into the
     level-0 slide mask at its box (int() truncated like :262-266).  `masks[i]` is uint8 [y1-y0, x1-x0] on the
     slide's device.  slide_mask: zero-initialised uint8 [SH,SW]."""
+    _check_u8(slide_mask, "slide_mask", 2)
     sh, sw = slide_mask.shape
     dev = slide_mask.device
+    st = slide_mask.untyped_storage()
+    if st.nbytes() - slide_mask.storage_offset() < ((sh * sw + 3) // 4) * 4 or slide_mask.data_ptr() % 4:
+        raise RuntimeError("slide_mask must be 4-byte aligned with storage up to the next multiple of 4 bytes (32-bit merge words)")
     ib = np.array([[int(b[0]), int(b[1]), int(b[2]), int(b[3])] for b in boxes], np.int32).reshape(-1, 4)
     sizes = [(int(b[3] - b[1])) * (int(b[2] - b[0])) for b in ib]
     for m, b, s in zip(masks, ib, sizes):
-        if m.dtype != torch.uint8 or m.numel() != s:
-            raise RuntimeError("class map of box %s has the wrong size/dtype" % (b.tolist(),))
+        if m.dtype != torch.uint8 or m.numel() != s or m.device != dev:
+            raise RuntimeError("class map of box %s has the wrong size / dtype / device" % (b.tolist(),))
     offs = np.zeros(len(ib), np.int64)
     if len(ib):
         offs[1:] = np.cumsum(sizes)[:-1]
     flat = torch.cat([m.reshape(-1) for m in masks]) if len(masks) else torch.zeros(0, dtype=torch.uint8, device=dev)
     d_boxes = torch.from_numpy(ib).to(dev)
     d_offs = torch.from_numpy(offs).to(dev)
-    rc = _lib.lib().espnet_stitch_boxes(slide_mask.data_ptr(), sh, sw, stitch_y_limit(sw, sh, ws), d_boxes.data_ptr(),
-                                        d_offs.data_ptr(), flat.data_ptr(), len(ib), _stream(dev))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().espnet_stitch_boxes(slide_mask.data_ptr(), sh, sw, stitch_y_limit(sw, sh, ws), d_boxes.data_ptr(),
+                                            d_offs.data_ptr(), flat.data_ptr(), len(ib), _stream(dev))
     _lib.check(rc, None, "espnet_stitch_boxes")
     return slide_mask
 
 
-def stitch_grid(slide_mask: torch.Tensor, tile_masks: torch.Tensor, grid: TileGrid, row0: int, rows: int, ws: int = 2400):
-    """T3 for the regular tile grid, gather form.  tile_masks: uint8 [rows*n_x, win_y, win_x]."""
-    sh, sw = slide_mask.shape
-    rc = _lib.lib().espnet_stitch_grid(slide_mask.data_ptr(), sh, sw, stitch_y_limit(sw, sh, ws), tile_masks.data_ptr(),
-                                       grid.n_x, grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, row0, rows,
-                                       _stream(slide_mask.device))
-    _lib.check(rc, None, "espnet_stitch_grid")
+def stitch_grid(slide_mask: torch.Tensor, tile_masks: torch.Tensor, grid: TileGrid, row0: int, rows: int, ws: int = 2400,
+                band_y0: int = 0, slide_h: Optional[int] = None):
+    """T3 for the regular tile grid, gather form.  tile_masks: uint8 [rows*n_x, win_y, win_x].  `slide_mask` is the whole
+    level-0 mask [SH,SW] (default) or, with `slide_h` given, a band buffer holding slide rows [band_y0, band_y0 + its height)."""
+    _check_u8(slide_mask, "slide_mask", 2)
+    _check_u8(tile_masks, "tile_masks", 3, slide_mask.device)
+    if tuple(tile_masks.shape) != (rows * grid.n_x, grid.win_y, grid.win_x):
+        raise RuntimeError("tile_masks must be [rows*n_x, win_y, win_x] = %s, got %s" % ((rows * grid.n_x, grid.win_y, grid.win_x), tuple(tile_masks.shape)))
+    bh, sw = slide_mask.shape
+    sh = bh if slide_h is None else int(slide_h)
+    with torch.cuda.device(slide_mask.device):
+        rc = _lib.lib().espnet_stitch_grid_band(slide_mask.data_ptr(), band_y0, bh, sh, sw, stitch_y_limit(sw, sh, ws), tile_masks.data_ptr(),
+                                                grid.n_x, grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, row0, rows,
+                                                _stream(slide_mask.device))
+    _lib.check(rc, None, "espnet_stitch_grid_band")
     return slide_mask
+
+
+def max_merge_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst = max(dst, src) element-wise on CUDA uint8 tensors of equal size (the overlap-strip merge of the band gather)."""
+    if dst.numel() != src.numel() or not dst.is_contiguous() or not src.is_contiguous() or dst.dtype != torch.uint8 or src.dtype != torch.uint8:
+        raise RuntimeError("max_merge_ wants two contiguous uint8 tensors of equal size")
+    with torch.cuda.device(dst.device):
+        rc = _lib.lib().espnet_max_merge_u8(dst.data_ptr(), src.data_ptr(), dst.numel(), _stream(dst.device))
+    _lib.check(rc, None, "espnet_max_merge_u8")
+    return dst
 
 
 def ds8_luts(slide_w: int, slide_h: int, ws: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -142,44 +185,126 @@ def ds8_luts(slide_w: int, slide_h: int, ws: int) -> Tuple[np.ndarray, np.ndarra
 
 def downsample8(level0: torch.Tensor, ws: int = 2400) -> torch.Tensor:
     """T4: the /8 label image the reference pastes window by window (before palette / blending)."""
+    _check_u8(level0, "level0", 2)
     sh, sw = level0.shape
     ys, xs = ds8_luts(sw, sh, ws)
     dev = level0.device
     d_ys, d_xs = torch.from_numpy(ys).to(dev), torch.from_numpy(xs).to(dev)
     out = torch.empty((len(ys), len(xs)), dtype=torch.uint8, device=dev)
-    rc = _lib.lib().espnet_downsample_lut(level0.data_ptr(), sh, sw, out.data_ptr(), len(ys), len(xs), d_ys.data_ptr(),
-                                          d_xs.data_ptr(), _stream(dev))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().espnet_downsample_lut(level0.data_ptr(), sh, sw, out.data_ptr(), len(ys), len(xs), d_ys.data_ptr(),
+                                              d_xs.data_ptr(), _stream(dev))
     _lib.check(rc, None, "espnet_downsample_lut")
     return out
 
 
+def gather_bands(band: Optional[torch.Tensor], grid: TileGrid, slide_h: int, slide_w: int, rank: int, world: int,
+                 merge=None, group=None) -> Tuple[Optional[torch.Tensor], dict]:
+    """The one exchange of the multi-GPU WSI path: every rank hands its band mask (slide rows
+    [y0_r, y1_r), `band_rows`) to rank 0.  Rank 0 allocates the level-0 mask, keeps its own band, receives the rows no earlier
+    band covers STRAIGHT INTO their place in the slide mask, and only the rows a band shares with its predecessors (the tile
+    overlap, win - stride rows) into a staging buffer that is max-merged (eval_wsi_segmentation.py:311-312).  Point-to-point
+    (NCCL send/recv over NVLink, grouped), no reduction over the whole mask.  Returns (level0 on rank 0 else None, stats)."""
+    import torch.distributed as dist
+    merge = merge or (lambda d, s: max_merge_(d, s))
+    bands = [band_rows(grid, slide_h, r, world) for r in range(world)]
+    stats = {"bytes_received": 0, "bytes_merged": 0}
+    if rank != 0:
+        _, rows, y0, y1 = bands[rank]
+        if rows and y1 > y0:
+            cov = max([b[3] for b in bands[:rank] if b[1]] + [0])
+            split = min(max(cov, y0), y1) - y0                      # band rows [0, split) overlap earlier bands
+            ops = []
+            if split > 0:
+                ops.append(dist.P2POp(dist.isend, band[:split], 0, group))
+            if split < y1 - y0:
+                ops.append(dist.P2POp(dist.isend, band[split:], 0, group))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return None, stats
+    level0 = torch.zeros((slide_h, slide_w), dtype=torch.uint8, device=band.device if band is not None else None)
+    _, rows, y0, y1 = bands[0]
+    cov = 0
+    if rows and y1 > y0:
+        level0[y0:y1].copy_(band)
+        cov = y1
+    ops, strips = [], []
+    for r in range(1, world):
+        _, rows, y0, y1 = bands[r]
+        if not rows or y1 <= y0:
+            continue
+        split = min(max(cov, y0), y1)
+        if split > y0:
+            st = torch.empty((split - y0, slide_w), dtype=torch.uint8, device=level0.device)
+            strips.append((y0, split, st))
+            ops.append(dist.P2POp(dist.irecv, st, r, group))
+        if split < y1:
+            ops.append(dist.P2POp(dist.irecv, level0[split:y1], r, group))      # zero-copy placement
+        stats["bytes_received"] += (y1 - y0) * slide_w
+        cov = max(cov, y1)
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for ya, yb, st in strips:
+        merge(level0[ya:yb], st)
+        stats["bytes_merged"] += (yb - ya) * slide_w
+    return level0, stats
+
+
 def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 512, mpp: float = 1.0, overlap: float = 0.1,
                   downsample: float = 1.0, ws: int = 2400, batch: int = 256, rank: int = 0, world: int = 1,
-                  reduce_to_rank0: bool = True):
+                  reduce_to_rank0: bool = True, slide_y0: int = 0, slide_h: Optional[int] = None, timings: Optional[dict] = None):
     """Overlapping-tile WSI segmentation (BASELINE.json config 4): T1 tiles -> ESPNet forward + arg-max per
-    tile -> T3 max-merge -> T4 /8 mask.  `slide_u8` is the resident BGR slide uint8 [SH,SW,3] (every rank holds
-    it, or at least its band).  With world > 1 the tile rows are sharded across ranks; the forward has no
-    collective, the only exchange is one max-reduce of the level-0 mask to rank 0.
-    Returns (level0 uint8 [SH,SW], ds8 uint8 [int(SH/8), int(SW/8)], n_local_tiles)."""
+    tile -> T3 max-merge -> T4 /8 mask.  `slide_u8` is the resident BGR slide uint8 [rows,SW,3]: the whole slide, or -- with
+    `slide_h` (full height) and `slide_y0` given -- just the rows [slide_y0, slide_y0 + rows) that this rank's band of tiles
+    reads (`band_rows`).  With world > 1 the tile rows are sharded across ranks; the forward has no collective; every rank
+    stitches its own band and `gather_bands` places the bands on rank 0.
+    Returns (level0 uint8 [SH,SW] on rank 0 (the rank's band mask [y1-y0,SW] elsewhere, or everywhere when
+    reduce_to_rank0=False), ds8 uint8 [int(SH/8), int(SW/8)] on rank 0, n_local_tiles)."""
     if downsample != 1.0:
         raise RuntimeError("only level-0 tiling (downsample 1) is wired to the resident-slide reader")
-    sh, sw = int(slide_u8.shape[0]), int(slide_u8.shape[1])
+    _check_u8(slide_u8, "slide_u8", 3)
+    sh = int(slide_u8.shape[0]) + slide_y0 if slide_h is None else int(slide_h)
+    sw = int(slide_u8.shape[1])
     dev = slide_u8.device
     grid = tile_grid(sw, sh, std_size, mpp, mpp, overlap, downsample)
     if grid.win_x % 8 or grid.win_y % 8:
         raise RuntimeError("tile size %dx%d is not a multiple of 8 (ESPNet needs it, Model.py cat at :373)" % (grid.win_x, grid.win_y))
-    row0, rows = shard_rows(grid.n_y, rank, world)
-    level0 = torch.zeros((sh, sw), dtype=torch.uint8, device=dev)
+    row0, rows, y0, y1 = band_rows(grid, sh, rank, world)
+    if rows and (slide_y0 > y0 or slide_y0 + int(slide_u8.shape[0]) < y1):
+        raise RuntimeError("slide_u8 holds rows [%d,%d) but this rank's tiles read rows [%d,%d)" % (slide_y0, slide_y0 + slide_u8.shape[0], y0, y1))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
+    if ev:
+        ev[0].record()
+    band = torch.zeros((y1 - y0, sw), dtype=torch.uint8, device=dev)
     n_local = rows * grid.n_x
     if n_local:
-        origins = torch.from_numpy(grid.origins(row0, rows)).to(dev)
+        org = grid.origins(row0, rows)
+        org[:, 1] -= slide_y0                              # tile origins relative to the resident rows
+        origins = torch.from_numpy(org).to(dev)
         masks = torch.empty((n_local, grid.win_y, grid.win_x), dtype=torch.uint8, device=dev)
+        # rows below the resident part are outside the SLIDE for the last band only, where zero padding is what read_region does
         for s in range(0, n_local, batch):
             e = min(s + batch, n_local)
             model.segment_tiles(slide_u8, origins[s:e], grid.win_y, grid.win_x, mean, std, out=masks[s:e])
-        stitch_grid(level0, masks, grid, row0, rows, ws)
+        if ev:
+            ev[1].record()
+        stitch_grid(band, masks, grid, row0, rows, ws, band_y0=y0, slide_h=sh)
+    elif ev:
+        ev[1].record()
+    if ev:
+        ev[2].record()
     if world > 1 and reduce_to_rank0:
-        import torch.distributed as dist
-        dist.reduce(level0, dst=0, op=dist.ReduceOp.MAX)
-    ds8 = downsample8(level0, ws) if (rank == 0 or not reduce_to_rank0) else None
-    return level0, ds8, n_local
+        level0, stats = gather_bands(band, grid, sh, sw, rank, world)
+    else:
+        level0, stats = band, {"bytes_received": 0, "bytes_merged": 0}
+        if world == 1 and (y0 != 0 or y1 != sh):           # tiles do not reach the last slide rows (cannot happen with T1's ceil)
+            level0 = torch.zeros((sh, sw), dtype=torch.uint8, device=dev)
+            level0[y0:y1].copy_(band)
+    if ev:
+        ev[3].record()
+    ds8 = downsample8(level0, ws) if (level0 is not None and tuple(level0.shape) == (sh, sw)) else None
+    if ev:
+        torch.cuda.synchronize(dev)
+        timings.update(forward_ms=ev[0].elapsed_time(ev[1]), stitch_ms=ev[1].elapsed_time(ev[2]), gather_ms=ev[2].elapsed_time(ev[3]), **stats)
+    return (level0 if level0 is not None else band), ds8, n_local

@@ -105,6 +105,13 @@ ESPNET_API size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W)
  * VisualizeResults_iou.py:107-128 -> Model.py:341-378 (FULL) / :273-304 (ENCODER). */
 ESPNET_API int espnet_forward(espnet_t* h, const espnet_forward_args* a);
 
+/* The same forward recorded once into a CUDA graph with THESE buffers (x, outputs, workspace stay owned by the caller and must
+ * stay valid and in place); espnet_graph_launch replays it on `stream` with one launch instead of ~30.  For the per-crop loop of
+ * VisualizeResults_iou.py:100-129 (batch 1), where the forward is launch-latency bound.  Repacking weights drops all graphs. */
+ESPNET_API int espnet_graph_capture(espnet_t* h, const espnet_forward_args* a, int* graph_id);
+ESPNET_API int espnet_graph_launch(espnet_t* h, int graph_id, void* stream);
+ESPNET_API int espnet_graph_destroy(espnet_t* h, int graph_id);
+
 /* Debug / parity taps: copies an internal stage of the LAST forward to `dst` (device, fp32 NCHW).
  * stage names follow the reference module names ("b1","level2_0","level2.1","b2","level3_0",
  * "level3.7","b3", "up_l3", "combine_l2_l3", "up_l2", "conv", ...).  *count receives elements. */
@@ -126,16 +133,26 @@ ESPNET_API int espnet_segment_host(espnet_t* h, const uint8_t* crops_host, int B
 /* T3 (eval_wsi_segmentation.py:259-316, annotation_handler.py:74-105): slide[y,x] = max(slide[y,x], mask_b[..])
  * for every box b = boxes[b] = (x0,y0,x1,y1) int32 level-0 px (may overhang the slide), masks packed
  * back to back (box b at mask_offsets[b], row pitch x1-x0).  Rows >= y_limit are left untouched
- * (the reference's `ymax > slide_width` window skip, :194).  slide must be zero-initialised by the caller. */
+ * (the reference's `ymax > slide_width` window skip, :194).  slide must be zero-initialised by the caller, 4-byte aligned,
+ * and its allocation must extend to the next multiple of 4 bytes (the merge works on 32-bit words; cudaMalloc and torch
+ * allocations always do). */
 ESPNET_API int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit,
                         const int32_t* boxes, const int64_t* mask_offsets, const uint8_t* masks,
                         int n_boxes, void* stream);
 
 /* Same merge for a regular tile grid (T1 order: tile k = j*n_x + i at (i*stride_x, j*stride_y)),
- * gather form, no atomics: every slide pixel takes the max over the tiles covering it. */
+ * gather form, no atomics: every slide pixel takes the max over the tiles covering it.  No limit on the slide height. */
 ESPNET_API int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit,
                        const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
                        int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream);
+/* The same into a BAND buffer [band_rows][slide_w] that holds slide rows [band_y0, band_y0 + band_rows): what a rank of a
+ * multi-GPU run stitches from its own tile rows without allocating the whole slide mask. */
+ESPNET_API int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int slide_h, int slide_w, int y_limit,
+                       const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
+                       int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream);
+/* dst[i] = max(dst[i], src[i]), n bytes: merge of the rows that two adjacent bands share (the tile-overlap strip) after the
+ * band gather; the element-wise max of eval_wsi_segmentation.py:311-312. */
+ESPNET_API int espnet_max_merge_u8(uint8_t* dst, const uint8_t* src, size_t n, void* stream);
 
 /* T4 (eval_wsi_segmentation.py:225-240): ds[y,x] = level0[ysrc[y], xsrc[x]] (or 0 where the LUT is <0).
  * The LUTs are computed on the host in double (espnet_ds8_lut) so that cv2's INTER_NEAREST index

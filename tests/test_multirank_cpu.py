@@ -1,8 +1,9 @@
-"""N > 1 path on CPU (gloo, world_size 2): the tile rows of a slide shard across ranks with no collective in the
-forward; the only exchange is the final max-reduce of the level-0 masks to rank 0 (wsi.segment_slide).
-The per-tile class maps are synthetic here (the forward itself needs the GPU); what is checked is the host logic a
-multi-GPU run relies on: shard_rows partitions the tile rows, TileGrid.origins enumerates the same tiles as the
-reference's scan_region loop, and max-merging per-rank band masks + MAX-reduce equals the single-process stitch."""
+"""N > 1 path on CPU (gloo, world_size 2 and 3): the tile rows of a slide shard across ranks with no collective in the
+forward; every rank stitches only its own band of slide rows and the only exchange is wsi.gather_bands:
+point-to-point, rows no earlier band covers are received straight into the slide mask, the tile-overlap rows are
+max-merged.  The per-tile class maps are synthetic here (the forward itself needs the GPU); what is checked is the host
+logic a multi-GPU run relies on: shard_rows / band_rows partition the slide, TileGrid.origins enumerates the same tiles as
+the reference's scan_region loop, and the gathered mask equals the single-process stitch."""
 import os
 import socket
 
@@ -51,27 +52,30 @@ def _worker(rank, world, port, sw, sh, ov, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         grid = wsi.tile_grid(sw, sh, 64, 1.0, 1.0, ov, 1.0)
-        row0, rows = wsi.shard_rows(grid.n_y, rank, world)
+        row0, rows, y0, y1 = wsi.band_rows(grid, sh, rank, world)
         ylim = wsi.stitch_y_limit(sw, sh, 2400)
-        local = torch.from_numpy(_band_mask(sw, sh, grid, row0, rows, ylim))
-        dist.reduce(local, dst=0, op=dist.ReduceOp.MAX)          # the one exchange of the WSI path
+        # the rank's band buffer holds ONLY slide rows [y0, y1)
+        band = torch.from_numpy(_band_mask(sw, sh, grid, row0, rows, ylim)[y0:y1].copy())
+        level0, stats = wsi.gather_bands(band, grid, sh, sw, rank, world, merge=lambda d, s: d.copy_(torch.maximum(d, s)))
         counts = torch.tensor([rows * grid.n_x], dtype=torch.int64)
         dist.all_reduce(counts)
         if rank == 0:
-            q.put((local.numpy(), int(counts.item())))
+            q.put((level0.numpy(), int(counts.item()), stats))
+        else:
+            assert level0 is None
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("sw,sh,ov", [(500, 380, 0.1), (333, 420, 0.5)])
-def test_two_rank_band_sharding_equals_single_process(sw, sh, ov):
+@pytest.mark.parametrize("sw,sh,ov,world", [(500, 380, 0.1, 2), (333, 420, 0.5, 2), (300, 700, 0.5, 3), (200, 130, 0.1, 3)])
+def test_band_sharding_and_gather_equal_single_process(sw, sh, ov, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, sw, sh, ov, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, sw, sh, ov, q)) for r in range(world)]
     for p in procs:
         p.start()
-    merged, n_tiles = q.get(timeout=120)
+    merged, n_tiles, stats = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -79,8 +83,21 @@ def test_two_rank_band_sharding_equals_single_process(sw, sh, ov):
     # the sharded tile set is the reference's tile set (detect_glomus_test.py:264-304 restated in the oracle)
     origins, n_x, n_y, win_x, win_y, stride_x, stride_y = W.tile_grid(sw, sh, 64, 1.0, 1.0, ov, 1.0)
     assert (grid.n_x, grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y) == (n_x, n_y, win_x, win_y, stride_x, stride_y)
-    bands = [wsi.shard_rows(grid.n_y, r, 2) for r in range(2)]
+    bands = [wsi.shard_rows(grid.n_y, r, world) for r in range(world)]
     assert np.array_equal(np.concatenate([grid.origins(r0, n) for r0, n in bands]), origins)
     assert n_tiles == grid.count
     single = _band_mask(sw, sh, grid, 0, grid.n_y, wsi.stitch_y_limit(sw, sh, 2400))
     assert np.array_equal(merged, single)
+    # only the overlap rows went through the merge, and nobody shipped a whole-slide mask
+    geo = [wsi.band_rows(grid, sh, r, world) for r in range(world)]
+    assert stats["bytes_received"] == sum((y1 - y0) * sw for _, rows, y0, y1 in geo[1:] if rows)
+    assert stats["bytes_merged"] < stats["bytes_received"] or world == 1
+
+
+def test_band_rows_cover_the_slide_and_overlap_by_the_tile_overlap():
+    grid = wsi.tile_grid(40000, 30000, 512, 1.0, 1.0, 0.1, 1.0)
+    geo = [wsi.band_rows(grid, 30000, r, 8) for r in range(8)]
+    assert geo[0][2] == 0 and geo[-1][3] == 30000
+    for a, b in zip(geo, geo[1:]):
+        assert a[3] - b[2] == grid.win_y - grid.stride_y == 52          # adjacent bands share exactly the tile overlap
+    assert sum(g[1] for g in geo) == grid.n_y
