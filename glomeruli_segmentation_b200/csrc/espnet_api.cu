@@ -1326,6 +1326,11 @@ int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_lim
     stitch_boxes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(slide_mask, slide_h, slide_w, y_limit, boxes,
                                                                (const long long*)mask_offsets, masks, n_boxes);
     LAUNCH_COUNT();
+    if (((size_t)slide_h * slide_w) & 3) {
+        stitch_boxes_tail_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(slide_mask, slide_h, slide_w, y_limit, boxes, (const long long*)mask_offsets,
+                                                                    masks, n_boxes);
+        LAUNCH_COUNT();
+    }
     return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
 }
 

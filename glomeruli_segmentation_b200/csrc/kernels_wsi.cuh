@@ -24,12 +24,14 @@ __global__ void __launch_bounds__(256) stitch_boxes_kernel(unsigned char* __rest
     if (cx1 <= cx0 || cy1 <= cy0) return;
     const unsigned char* m = masks + offs[bi];
     unsigned int* words = reinterpret_cast<unsigned int*>(slide);
+    const size_t total = (size_t)SH * SW;
     for (int y = cy0 + blockIdx.y; y < cy1; y += gridDim.y) {
         const size_t row = (size_t)y * SW;
         const size_t f0 = row + cx0, f1 = row + cx1;          // flat byte range [f0,f1)
         const size_t w0 = f0 >> 2, w1 = (f1 - 1) >> 2;
         const unsigned char* mrow = m + (size_t)(y - y0) * bw;        // mrow[x - x0] for slide column x
         for (size_t w = w0 + threadIdx.x; w <= w1; w += 256) {
+            if (4 * w + 4 > total) continue;       // the partial last word of the buffer: stitch_boxes_tail_kernel (no access past the end)
             unsigned int cand = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -47,6 +49,23 @@ __global__ void __launch_bounds__(256) stitch_boxes_kernel(unsigned char* __rest
             }
         }
     }
+}
+
+// The last SH*SW % 4 bytes of the slide mask do not fill a 32-bit merge word: one thread per such byte walks all boxes
+// (runs after stitch_boxes_kernel on the same stream, so nothing races) -- no word access ever crosses the buffer's end.
+__global__ void stitch_boxes_tail_kernel(unsigned char* __restrict__ slide, int SH, int SW, int y_limit, const int32_t* __restrict__ boxes,
+                                         const long long* __restrict__ offs, const unsigned char* __restrict__ masks, int n_boxes) {
+    const size_t total = (size_t)SH * SW;
+    const size_t f = (total & ~(size_t)3) + threadIdx.x;
+    if (f >= total) return;
+    const int y = (int)(f / SW), x = (int)(f % SW);
+    if (y >= y_limit) return;
+    int best = slide[f];
+    for (int bi = 0; bi < n_boxes; ++bi) {
+        const int x0 = boxes[4 * bi], y0 = boxes[4 * bi + 1], x1 = boxes[4 * bi + 2], y1 = boxes[4 * bi + 3];
+        if (x >= x0 && x < x1 && y >= y0 && y < y1) best = max(best, (int)masks[offs[bi] + (size_t)(y - y0) * (x1 - x0) + (x - x0)]);
+    }
+    slide[f] = (unsigned char)best;
 }
 
 // T3, gather form for the regular T1 grid (detect_glomus_test.py:268-271): tile k = j*n_x + i sits at

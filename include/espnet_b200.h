@@ -133,9 +133,8 @@ ESPNET_API int espnet_segment_host(espnet_t* h, const uint8_t* crops_host, int B
 /* T3 (eval_wsi_segmentation.py:259-316, annotation_handler.py:74-105): slide[y,x] = max(slide[y,x], mask_b[..])
  * for every box b = boxes[b] = (x0,y0,x1,y1) int32 level-0 px (may overhang the slide), masks packed
  * back to back (box b at mask_offsets[b], row pitch x1-x0).  Rows >= y_limit are left untouched
- * (the reference's `ymax > slide_width` window skip, :194).  slide must be zero-initialised by the caller, 4-byte aligned,
- * and its allocation must extend to the next multiple of 4 bytes (the merge works on 32-bit words; cudaMalloc and torch
- * allocations always do). */
+ * (the reference's `ymax > slide_width` window skip, :194).  slide must be zero-initialised by the caller and 4-byte aligned
+ * (the merge works on 32-bit words; the last slide_h*slide_w % 4 bytes are merged byte-wise, nothing past the end is touched). */
 ESPNET_API int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit,
                         const int32_t* boxes, const int64_t* mask_offsets, const uint8_t* masks,
                         int n_boxes, void* stream);

