@@ -23,6 +23,7 @@
 #include "kernels_wsi.cuh"
 #include "kernels_frontend.cuh"
 #include "kernels_dec.cuh"
+#include "kernels_tail_generic.cuh"
 
 using namespace espnet;
 
@@ -91,6 +92,7 @@ struct espnet_handle {
     std::map<std::string, StageRef> stages;
     int fp32_impl = 1;     // fp32 mode: 1 (default) = tensor cores with 3-term fp16 operand splits (fp32-equivalent), 0 = CUDA-core FMA kernels ("fp32_impl")
     int tc_pair = 0;       // branch stage on tensor cores: 1 = CTA pairs, cta_group::2 M = 256 MMAs (kernels_tc_pair.cuh), 0 = one CTA per tile ("tc_pair")
+    int tail_impl = 0;     // 1 = run the generic run-time-class-count tail kernels even for 5 / 20 classes ("tail_impl", cross-check)
     int dec_impl = 1;      // decoder tail: 1 = 4 pixels per thread (dec_c4_kernel), 0 = 1 pixel per thread ("dec_impl")
     int l2_reverse = 1;    // 1x1 reduce walks its tiles against the order of the kernel that produced its input (L2 reuse)
     int tc_reduce = 1;     // f16tc mode: 1 = 1x1 reduce on tensor cores, 0 = CUDA-core fp32 reduce rounded to fp16 ("tc_reduce")
@@ -834,6 +836,84 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
     return ESPNET_OK;
 }
 
+// The same tail for any class count (kernels_tail_generic.cuh): classes other than 5 / 20, or option "tail_impl" = 1.
+int run_tail_generic(espnet_t* h, const espnet_forward_args* a, const Workspace& L, float* ws, cudaStream_t st) {
+    const int B = a->B, H = a->H, W = a->W, nc = h->classes;
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+    const Packed& pk = h->pk;
+    const float* P = h->dparams;
+    const bool full = h->net == ESPNET_NET_FULL;
+    auto grid1d = [&](size_t n) { int g = (int)((n + 255) / 256); if (g > 8 * h->num_sms) g = 8 * h->num_sms; return g < 1 ? 1 : g; };
+    {
+        Head3Params<0> p{};
+        p.in = ws + L.out2cat; p.w = P + pk.cls_w; p.B = B; p.H8 = H8; p.W8 = W8;
+        if (full) { p.bn_s = P + pk.br_s; p.bn_t = P + pk.br_t; p.wt = P + pk.up3_w; p.up_out = ws + L.up3; p.enc_out = nullptr; }
+        else p.enc_out = a->logits ? a->logits : ws + L.enc;
+        const size_t smem = ((size_t)256 * nc + (size_t)nc * nc * 4 + 2 * nc) * sizeof(float);
+        int rc = set_smem(h, g_head3_kernel, 227 * 1024);
+        if (rc) return rc;
+        { ProfScope _ps(h, "head3", st); g_head3_kernel<<<grid1d((size_t)B * H8 * W8), 256, smem, st>>>(p, nc); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        if (!full) {
+            h->stages["encoder.classifier"] = {p.enc_out, (size_t)B * nc * H8 * W8};
+            if (a->mask) {
+                dim3 g((W + 31) / 32, (H + 7) / 8, B);
+                { ProfScope _ps(h, "upsample8_argmax", st); g_upsample8_argmax_kernel<<<g, 256, 0, st>>>(p.enc_out, nc, B, H8, W8, a->mask); }
+                LAUNCH_COUNT();
+                CUDA_TRY(h, cudaPeekAtLastError());
+            }
+            return ESPNET_OK;
+        }
+        h->stages["up_l3"] = {ws + L.up3, (size_t)B * nc * H4 * W4};
+    }
+    {
+        DecAParams<0> p{};
+        p.out1cat = ws + L.out1cat; p.up3 = ws + L.up3; p.w = P + pk.l3c_w;
+        p.s = P + pk.c0_s; p.t = P + pk.c0_t; p.a = P + pk.c0_a;
+        p.tout = ws + L.t10; p.B = B; p.H4 = H4; p.W4 = W4;
+        const size_t smem = ((size_t)131 * nc + 6 * nc) * sizeof(float);
+        int rc = set_smem(h, g_dec_a_kernel, 227 * 1024);
+        if (rc) return rc;
+        { ProfScope _ps(h, "dec_a", st); g_dec_a_kernel<<<grid1d((size_t)B * H4 * W4), 256, smem, st>>>(p, nc); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        h->stages["combine_l2_l3.0"] = {ws + L.t10, (size_t)B * 2 * nc * H4 * W4};
+    }
+    {
+        DecBParams<0> p{};
+        p.tin = ws + L.t10; p.w = P + pk.c1_w;
+        p.s = P + pk.c1_s; p.t = P + pk.c1_t; p.a = P + pk.c1_a;
+        p.wt = P + pk.up2_w;
+        p.s2 = P + pk.u2_s; p.t2 = P + pk.u2_t; p.a2 = P + pk.u2_a;
+        p.comb = ws + L.comb; p.B = B; p.H4 = H4; p.W4 = W4;
+        const size_t smem = ((size_t)2 * nc * 9 * nc + (size_t)nc * nc * 4 + 6 * nc) * sizeof(float);
+        int rc = set_smem(h, g_dec_b_kernel, 227 * 1024);
+        if (rc) return rc;
+        { ProfScope _ps(h, "dec_b", st); g_dec_b_kernel<<<grid1d((size_t)B * H4 * W4), 256, smem, st>>>(p, nc); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        h->stages["up_l2"] = {ws + L.comb, (size_t)B * nc * H2 * W2};
+    }
+    {
+        DecCParams<0> p{};
+        p.comb = ws + L.comb; p.out0cat = ws + L.out0cat; p.w = P + pk.cv_w;
+        p.s = P + pk.cv_s; p.t = P + pk.cv_t; p.a = P + pk.cv_a;
+        p.wt = P + pk.clsT_w;
+        p.logits = a->logits; p.mask = a->mask; p.prob_acc = a->prob_acc;
+        p.prob_init = a->prob_init; p.mask_from_prob = a->mask_from_prob;
+        p.B = B; p.H2 = H2; p.W2 = W2;
+        const size_t smem = ((size_t)(nc + 19) * 9 * nc + (size_t)nc * nc * 4 + 3 * nc) * sizeof(float);
+        int rc = set_smem(h, g_dec_c_kernel, 227 * 1024);
+        if (rc) return rc;
+        dim3 g((W2 + 31) / 32, (H2 + 7) / 8, B);
+        { ProfScope _ps(h, "dec_c", st); g_dec_c_kernel<<<g, 256, smem, st>>>(p, nc); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+    }
+    return ESPNET_OK;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -849,8 +929,9 @@ const char* espnet_last_error(const espnet_t* h) { return h ? h->err.c_str() : g
 int espnet_create(int classes, int p, int q, int net, int device, espnet_t** out) {
     if (!out) return fail(nullptr, ESPNET_EINVAL, "espnet_create: out is NULL");
     *out = nullptr;
-    if (classes != 5 && classes != 20)
-        return fail(nullptr, ESPNET_ESHAPE, "espnet_create: classes must be 5 or 20 (kernels are instantiated for those)");
+    if (classes < 1 || classes > kMaxClasses)
+        return fail(nullptr, ESPNET_ESHAPE, "espnet_create: classes must be in [1, " + std::to_string(kMaxClasses) + "] (5 and 20 run compile-time "
+                                            "specialised tail kernels, every other count the run-time generic ones)");
     if (p < 1 || q < 1) return fail(nullptr, ESPNET_EINVAL, "espnet_create: p and q must be >= 1 (the reference forward needs one block per level)");
     if (net != ESPNET_NET_FULL && net != ESPNET_NET_ENCODER) return fail(nullptr, ESPNET_EINVAL, "espnet_create: bad net");
     int ndev = 0;
@@ -902,6 +983,7 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "fp32_impl") == 0 && value >= 0 && value <= 1) { h->fp32_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "dec_impl") == 0 && value >= 0 && value <= 1) { h->dec_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "tail_impl") == 0 && value >= 0 && value <= 1) { h->tail_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_pair") == 0 && value >= 0 && value <= 1) { h->tc_pair = value; return ESPNET_OK; }
     if (std::strcmp(key, "l2_reverse") == 0 && value >= 0 && value <= 1) { h->l2_reverse = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 2) { h->tc_reduce = value; return ESPNET_OK; }
@@ -1124,8 +1206,9 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
         h->stages["b3"] = {ws + L.out2cat, (size_t)B * 256 * H8 * W8};
     }
     // ---- S7..S10 heads / decoder -------------------------------------------------------------------
-    if (h->classes == 5) return run_tail<5>(h, a, L, ws, st);
-    return run_tail<20>(h, a, L, ws, st);
+    if (h->classes == 5 && !h->tail_impl) return run_tail<5>(h, a, L, ws, st);
+    if (h->classes == 20 && !h->tail_impl) return run_tail<20>(h, a, L, ws, st);
+    return run_tail_generic(h, a, L, ws, st);
 }
 
 // One forward with FIXED buffers recorded into a CUDA graph: ~30 kernel launches become one cudaGraphLaunch, which is what the

@@ -82,7 +82,9 @@ typedef struct {
     void* stream;         /* cudaStream_t                                                                   */
 } espnet_forward_args;
 
-/* Replaces Model.ESPNet(classes,p,q) / Model.ESPNet_Encoder(classes,p,q) construction (Model.py:246,311). */
+/* Replaces Model.ESPNet(classes,p,q) / Model.ESPNet_Encoder(classes,p,q) construction (Model.py:246,311).  Any classes in
+ * [1, 48] (the reference's default 20 and the shipped checkpoints' 5 run compile-time specialised tail kernels, other counts
+ * the generic run-time ones); p, q >= 1. */
 ESPNET_API int espnet_create(int classes, int p, int q, int net, int device, espnet_t** out);
 ESPNET_API void espnet_destroy(espnet_t* h);
 ESPNET_API const char* espnet_last_error(const espnet_t* h); /* h may be NULL: last error of failed create */
@@ -97,7 +99,8 @@ ESPNET_API int espnet_set_mode(espnet_t* h, int mode);            /* ESPNET_MODE
  * loads, 2 TMA-staged shared-memory halo tiles); "tc_reduce" (tensor-core modes: 1 = reduce convs on tensor cores, 0 = CUDA
  * cores); "tc_pair" (tensor-core branch stage: 0 = one CTA per MMA tile (default), 1 = clusters of two CTAs with
  * tcgen05 cta_group::2 M = 256 MMAs -- bit-identical results); "l2_reverse" (1x1 reduce walks its tiles against the
- * producer's order to start on the L2-resident part, default 1); "dec_impl" (decoder tail: 1 = 4 pixels per thread). */
+ * producer's order to start on the L2-resident part, default 1); "dec_impl" (decoder tail: 1 = 4 pixels per thread); "tail_impl" (1 = generic run-time-class-count tail kernels even for 5 / 20
+ * classes; bit-identical to the scalar specialised ones). */
 ESPNET_API int espnet_set_option(espnet_t* h, const char* key, int value);
 ESPNET_API size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W);
 

@@ -349,12 +349,12 @@ def test_stitch_grid_slide_taller_than_65535_rows():
 
 def test_stitch_boxes_never_touches_bytes_past_an_odd_sized_mask():
     """SH*SW not a multiple of 4 -- the mask is a view whose end is followed by live data; those bytes survive."""
-    sh, sw = 33, 31                                            # 1023 bytes
+    sh, sw = 31, 33                                            # 1023 bytes; wider than tall, so the reference's ymax > width skip stays out of it
     buf = torch.full((sh * sw + 9,), 77, dtype=torch.uint8, device=DEV)
     view = buf[4:4 + sh * sw].view(sh, sw)
     view.zero_()
     rng = np.random.default_rng(2)
-    boxes = [[20, 25, 40, 40, 1.0], [0, 30, 31, 33, 1.0], [28, 31, 31, 33, 1.0]]
+    boxes = [[20, 25, 40, 40, 1.0], [0, 28, 33, 31, 1.0], [30, 29, 33, 31, 1.0]]
     masks = [rng.integers(1, 5, (int(b[3] - b[1]), int(b[2] - b[0]))).astype(np.uint8) for b in boxes]
     wsi.stitch_boxes(view, boxes, [torch.from_numpy(m).to(DEV) for m in masks], ws=8)
     exp, _ = W.stitch_slide(boxes, masks, sw, sh, 8)
@@ -403,3 +403,58 @@ def test_captured_graph_replays_the_same_forward(fold_sd, net):
     m.load_state_dict(sd2)
     with pytest.raises(RuntimeError, match="capture again"):
         g.run()
+
+
+@pytest.mark.parametrize("classes", [1, 2, 7, 20, 33])
+@pytest.mark.parametrize("net", ["full", "encoder"])
+def test_any_number_of_classes(classes, net):
+    """Model.py:246,311 take any `classes`; 5 and 20 run the specialised tail kernels, the rest the generic run-time ones
+    (kernels_tail_generic.cuh).  Logits against the oracle, masks = arg-max of the logits with the lowest-index tie rule."""
+    from glomeruli_segmentation_b200 import ESPNet_Encoder
+    sd = O.random_state_dict(classes, 2, 2, seed=classes)
+    mean, std = FOLD_MEAN_STD[2]
+    u8 = O.synth_crops("D2", 2, 64, 88, seed=classes, sigma=3.0)
+    x = torch.from_numpy(O.normalise_bgr_u8(u8, mean, std))
+    if net == "full":
+        m = ESPNet(classes, 2, 2); m.load_state_dict(sd, strict=True)
+        ref = O.espnet_forward(sd, x)
+        lg = torch.empty((2, classes, 64, 88), device=DEV)
+    else:
+        esd = O.encoder_state_dict(sd)
+        m = ESPNet_Encoder(classes, 2, 2); m.load_state_dict(esd, strict=True)
+        ref = O.espnet_encoder_forward(esd, x)
+        lg = torch.empty((2, classes, 8, 11), device=DEV)
+    m = m.to(DEV).eval()
+    mask = m.segment(torch.from_numpy(u8).to(DEV), mean, std, logits=lg)
+    scale = max(1.0, ref.abs().max().item())
+    assert (lg.cpu() - ref).abs().max().item() <= 1e-3 * scale
+    assert (m(x.to(DEV)).cpu() - ref).abs().max().item() <= 1e-3 * scale
+    if net == "full":
+        assert torch.equal(mask, lg.max(1)[1].to(torch.uint8))
+    else:
+        up = O.upsample8_bilinear(lg.cpu())
+        assert (mask.cpu().numpy() == O.argmax_mask(up)).mean() >= 0.999       # bilinear weights differ in the last ulp only at ties
+
+
+@pytest.mark.parametrize("net", ["full", "encoder"])
+def test_generic_tail_is_bit_identical_to_the_specialised_scalar_tail(fold_sd, net):
+    from glomeruli_segmentation_b200 import ESPNet_Encoder
+    sd = fold_sd(2)
+    mean, std = FOLD_MEAN_STD[2]
+    if net == "full":
+        mk = lambda: ESPNet(5, 2, 8)
+        state = sd
+    else:
+        mk = lambda: ESPNet_Encoder(5, 2, 8)
+        state = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    a, b = mk(), mk()
+    a.load_state_dict(state, strict=True); b.load_state_dict(state, strict=True)
+    a = a.to(DEV).eval().set_option("dec_impl", 0)            # specialised one-pixel-per-thread kernels
+    b = b.to(DEV).eval().set_option("tail_impl", 1)           # generic run-time-nc kernels
+    u8 = torch.from_numpy(O.synth_crops("D2", 2, 136, 200, seed=4, sigma=3.0)).to(DEV)
+    shape = (2, 5, 136, 200) if net == "full" else (2, 5, 17, 25)
+    la, lb = torch.empty(shape, device=DEV), torch.empty(shape, device=DEV)
+    ma = a.segment(u8, mean, std, logits=la)
+    mb = b.segment(u8, mean, std, logits=lb)
+    assert torch.equal(la, lb)
+    assert (ma == mb).float().mean().item() >= (1.0 if net == "full" else 0.9999)
