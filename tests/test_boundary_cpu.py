@@ -70,7 +70,8 @@ def test_no_cpu_fallback():
         rc = _lib.lib().espnet_create(5, 2, 8, _lib.NET_FULL, 0, C.byref(h))
         assert rc == _lib.ECUDA and b"no CPU fallback" in _lib.lib().espnet_last_error(None)
     h = C.c_void_p()
-    assert _lib.lib().espnet_create(7, 2, 8, _lib.NET_FULL, 0, C.byref(h)) == _lib.ESHAPE
+    assert _lib.lib().espnet_create(0, 2, 8, _lib.NET_FULL, 0, C.byref(h)) == _lib.ESHAPE      # classes must be in [1, 48]
+    assert _lib.lib().espnet_create(49, 2, 8, _lib.NET_FULL, 0, C.byref(h)) == _lib.ESHAPE
     assert _lib.lib().espnet_create(5, 0, 8, _lib.NET_FULL, 0, C.byref(h)) == _lib.EINVAL
 
 
