@@ -596,10 +596,20 @@ def measure_wsi(ctx, args, steps, warmup):
     slide = synth_slide_rows(ctx.dev, sw, y0, y1)
     batch = args.batch or 256
     tm = {}
+    gather, gather_note = None, "single GPU"
+    if ctx.world > 1:
+        if args.gather == "p2p":
+            try:        # collective; raises on EVERY rank or on none
+                gather = wsi.PeerGather(grid, sh, sw, ctx.rank, ctx.world, ctx.dev)
+                gather_note = "p2p: stitch kernels write the bands into rank 0's slide mask through CUDA-IPC mappings (NVLink), overlap strips max-merged"
+            except RuntimeError as e:
+                gather_note = "nccl send/recv (peer mapping unavailable: %s)" % str(e)[:120]
+        else:
+            gather_note = "nccl send/recv of the band masks, overlap strips max-merged"
 
     def step():
         return wsi.segment_slide(model, slide, mean, std, std_size=512, mpp=1.0, overlap=args.overlap, batch=batch, rank=ctx.rank,
-                                 world=ctx.world, reduce_to_rank0=True, slide_y0=y0, slide_h=sh, timings=tm)
+                                 world=ctx.world, reduce_to_rank0=True, slide_y0=y0, slide_h=sh, timings=tm, gather=gather)
     for _ in range(warmup):
         step()
     sampler = ClockSampler(ctx.local)
@@ -630,12 +640,12 @@ def measure_wsi(ctx, args, steps, warmup):
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": DTYPE[args.mode], "data": "synthetic",
         "config": {"workload": "synthetic %dx%d px BGR u8 slide (each rank holds the rows of its band), T1 tiler 512 px / overlap %.2f -> %d tiles (%dx%d), "
-                               "full ESPNet(5,2,8) fold1 + arg-max per tile, per-rank band stitch (T3), point-to-point band gather to rank 0 with "
-                               "max-merged overlap strips, T4 /8 mask" % (sw, sh, args.overlap, grid.count, grid.n_x, grid.n_y),
+                               "full ESPNet(5,2,8) fold1 + arg-max per tile, per-rank band stitch (T3) placed on rank 0, "
+                               "overlap strips max-merged, T4 /8 mask" % (sw, sh, args.overlap, grid.count, grid.n_x, grid.n_y),
                    "tile_batch": batch, "mode": args.mode, "l2": "slide band (%.1f GB) and tile activations exceed the 126 MB L2" % ((y1 - y0) * sw * 3 / 1e9)},
         "tiles_per_s": grid.count * steps / (ms * 1e-3), "tile_mpx_per_s": grid.count * 0.262144 * steps / (ms * 1e-3),
         "phases_ms_max_over_ranks": {"tiles_forward": fwd, "band_gather": gather, "band_gather_share": gather / (ms / steps) if ms else None},
-        "gather_bytes_received_rank0": tm.get("bytes_received"), "gather_bytes_max_merged": tm.get("bytes_merged"),
+        "gather": gather_note, "gather_bytes_received_rank0": tm.get("bytes_received"), "gather_bytes_max_merged": tm.get("bytes_merged"),
         "gpu_launches": launches, "clocks": clocks, "ds8_class_histogram": hist,
     }
 
@@ -729,6 +739,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="headline workload only (no nested records)")
     ap.add_argument("--slide", default="40000x30000", help="wsi: synthetic slide WxH in level-0 pixels (BASELINE configs[3])")
     ap.add_argument("--overlap", type=float, default=0.1, help="wsi: tile overlap ratio (detect_glomus_test.py default)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="wsi at N > 1: how the band masks reach rank 0")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--depth", type=int, default=3, help="device slots of the host pipeline used for the e2e metric")
     ap.add_argument("--mode", default="fp32", choices=["fp32", "f16tc"],

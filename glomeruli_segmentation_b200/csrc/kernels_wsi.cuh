@@ -74,9 +74,13 @@ __global__ void stitch_boxes_tail_kernel(unsigned char* __restrict__ slide, int 
 // band sharding); pixels no resident tile covers are left untouched.  The output buffer holds slide rows
 // [out_y0, out_y0 + out_rows) (a rank's band, or the whole slide with out_y0 = 0); grid.y strides over the rows,
 // so slides taller than 65535 px need no special casing.
+//
+// overwrite = 0: out = max(out, stitched) (the buffer is zero-initialised or already holds other tiles' pixels);
+// overwrite = 1: every pixel of the covered rows is WRITTEN (0 where no tile covers it) and never read -- the form used when
+// `out` is another GPU's memory mapped over NVLink (P2P band placement: a remote read-modify-write would cost a round trip).
 __global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restrict__ out, int out_y0, int out_rows, int SH, int SW, int y_limit,
                                                           const unsigned char* __restrict__ tiles, int n_x, int n_y,
-                                                          int win_x, int win_y, int sx, int sy, int row0, int rows) {
+                                                          int win_x, int win_y, int sx, int sy, int row0, int rows, int overwrite) {
     const int ylo = max(row0 * sy, out_y0);
     const int yhi = min(min(min((row0 + rows - 1) * sy + win_y, SH), y_limit), out_y0 + out_rows);
     const size_t tile_sz = (size_t)win_x * win_y;
@@ -100,10 +104,9 @@ __global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restr
                     best = max(best, v);
                 }
             }
-            if (best >= 0) {
-                unsigned char* d = out + (size_t)(y - out_y0) * SW + x;
-                *d = (unsigned char)max((int)*d, best);
-            }
+            unsigned char* d = out + (size_t)(y - out_y0) * SW + x;
+            if (overwrite) *d = (unsigned char)max(best, 0);
+            else if (best >= 0) *d = (unsigned char)max((int)*d, best);
         }
     }
 }

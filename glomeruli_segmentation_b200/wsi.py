@@ -141,19 +141,22 @@ def stitch_boxes(slide_mask: torch.Tensor, boxes: Sequence[Sequence[float]], mas
 
 
 def stitch_grid(slide_mask: torch.Tensor, tile_masks: torch.Tensor, grid: TileGrid, row0: int, rows: int, ws: int = 2400,
-                band_y0: int = 0, slide_h: Optional[int] = None):
+                band_y0: int = 0, slide_h: Optional[int] = None, overwrite: bool = False):
     """T3 for the regular tile grid, gather form.  tile_masks: uint8 [rows*n_x, win_y, win_x].  `slide_mask` is the whole
-    level-0 mask [SH,SW] (default) or, with `slide_h` given, a band buffer holding slide rows [band_y0, band_y0 + its height)."""
+    level-0 mask [SH,SW] (default) or, with `slide_h` given, a band buffer holding slide rows [band_y0, band_y0 + its height).
+    overwrite=True writes every pixel of the covered rows without reading the destination, which may then live on ANOTHER GPU
+    (a CUDA-IPC mapping of rank 0's slide mask: the stitch kernel places the band over NVLink, see PeerGather)."""
     _check_u8(slide_mask, "slide_mask", 2)
-    _check_u8(tile_masks, "tile_masks", 3, slide_mask.device)
+    _check_u8(tile_masks, "tile_masks", 3, None if overwrite else slide_mask.device)
     if tuple(tile_masks.shape) != (rows * grid.n_x, grid.win_y, grid.win_x):
         raise RuntimeError("tile_masks must be [rows*n_x, win_y, win_x] = %s, got %s" % ((rows * grid.n_x, grid.win_y, grid.win_x), tuple(tile_masks.shape)))
     bh, sw = slide_mask.shape
     sh = bh if slide_h is None else int(slide_h)
-    with torch.cuda.device(slide_mask.device):
+    dev = tile_masks.device                    # the kernel runs where the tiles are
+    with torch.cuda.device(dev):
         rc = _lib.lib().espnet_stitch_grid_band(slide_mask.data_ptr(), band_y0, bh, sh, sw, stitch_y_limit(sw, sh, ws), tile_masks.data_ptr(),
                                                 grid.n_x, grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, row0, rows,
-                                                _stream(slide_mask.device))
+                                                int(overwrite), _stream(dev))
     _lib.check(rc, None, "espnet_stitch_grid_band")
     return slide_mask
 
@@ -250,15 +253,102 @@ def gather_bands(band: Optional[torch.Tensor], grid: TileGrid, slide_h: int, sli
     return level0, stats
 
 
+def band_plan(grid: TileGrid, slide_h: int, world: int):
+    """Per rank (y0, split, y1): band rows [y0, y1); rows [y0, split) are also covered by an earlier rank's band (they need the
+    max-merge), rows [split, y1) are this rank's to place."""
+    plan, cov = [], 0
+    for r in range(world):
+        _, rows, y0, y1 = band_rows(grid, slide_h, r, world)
+        if not rows or y1 <= y0:
+            plan.append((0, 0, 0))
+            continue
+        split = min(max(cov, y0), y1)
+        plan.append((y0, split, y1))
+        cov = max(cov, y1)
+    return plan
+
+
+class PeerGather:
+    """Zero-copy band placement over NVLink ("the stitch scatter kernel may write directly into a peer-mapped
+    slide buffer, which IS the fused scatter + gather").  Rank 0 allocates the level-0 slide mask and a small staging area for
+    the tile-overlap strips and exports both through CUDA IPC; every other rank maps them and its stitch kernel writes its
+    band's rows straight into rank 0's memory.  Only two tiny barriers and the max-merge of the strips (win - stride rows per
+    rank boundary) remain of the "gather".  Build once per (slide size, tiling, process group) -- the handle exchange is a
+    collective -- and pass to segment_slide(gather=...).  Raises if peer mapping is unavailable; callers then fall back to
+    gather_bands (NCCL send / recv)."""
+
+    def __init__(self, grid: TileGrid, slide_h: int, slide_w: int, rank: int, world: int, device: torch.device, ws: int = 2400, group=None):
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.grid, self.sh, self.sw, self.rank, self.world, self.group, self.dist = grid, slide_h, slide_w, rank, world, group, dist
+        self.plan = band_plan(grid, slide_h, world)
+        strip_rows = max([sp - y0 for y0, sp, _ in self.plan] + [1])
+        def all_ok(ok: bool, what: str):
+            # failures must be collective: a rank that raised alone would leave the others waiting in the next barrier
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                raise RuntimeError("PeerGather: %s failed on at least one rank (no CUDA IPC / peer access between the GPUs?)" % what)
+
+        with torch.cuda.device(device):
+            payload = [None, None]
+            if rank == 0:
+                self.level0 = torch.zeros((slide_h, slide_w), dtype=torch.uint8, device=device)       # rows nobody covers stay 0
+                self.strips = torch.zeros((world, strip_rows, slide_w), dtype=torch.uint8, device=device)
+                payload = [reduce_tensor(self.level0), reduce_tensor(self.strips)]
+            dist.broadcast_object_list(payload, src=0, group=group, device=device)
+            ok = True
+            try:
+                if rank != 0:
+                    (f0, a0), (f1, a1) = payload
+                    self.level0, self.strips = f0(*a0), f1(*a1)             # cudaIpcOpenMemHandle: rank 0's memory, peer access enabled
+                # every rank proves it can write the peer mapping before the first real use
+                self.strips[rank, 0, :8].fill_(rank + 1)
+                torch.cuda.synchronize(device)
+            except Exception:
+                ok = False
+            all_ok(ok, "mapping rank 0's slide mask")
+            dist.barrier(group=group)
+            ok = True
+            if rank == 0:
+                ok = self.strips[:, 0, 0].cpu().tolist() == [r + 1 for r in range(world)]
+                self.strips.zero_()
+                torch.cuda.synchronize(device)
+            all_ok(ok, "writing through the peer mapping")
+
+    def place(self, tile_masks: Optional[torch.Tensor], row0: int, rows: int, ws: int) -> dict:
+        """Collective: every rank stitches its tile rows into rank 0's slide mask (rows it owns) / strip staging (rows shared with
+        an earlier band); rank 0 merges the strips.  Returns byte counts."""
+        y0, split, y1 = self.plan[self.rank]
+        self.dist.barrier(group=self.group)          # rank 0 is done with the previous result
+        if rows and y1 > y0:
+            if split > y0:
+                stitch_grid(self.strips[self.rank, :split - y0], tile_masks, self.grid, row0, rows, ws, band_y0=y0, slide_h=self.sh, overwrite=True)
+            if y1 > split:
+                stitch_grid(self.level0[split:y1], tile_masks, self.grid, row0, rows, ws, band_y0=split, slide_h=self.sh, overwrite=True)
+        self.dist.barrier(group=self.group)          # every band has landed (kernel completion makes the peer writes visible)
+        stats = {"bytes_received": 0, "bytes_merged": 0, "gather": "p2p"}
+        if self.rank == 0:
+            for r, (a, sp, b) in enumerate(self.plan):
+                if r and sp > a:
+                    max_merge_(self.level0[a:sp], self.strips[r, :sp - a])
+                    stats["bytes_merged"] += (sp - a) * self.sw
+                if r:
+                    stats["bytes_received"] += (b - a) * self.sw
+        return stats
+
+
 def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 512, mpp: float = 1.0, overlap: float = 0.1,
                   downsample: float = 1.0, ws: int = 2400, batch: int = 256, rank: int = 0, world: int = 1,
-                  reduce_to_rank0: bool = True, slide_y0: int = 0, slide_h: Optional[int] = None, timings: Optional[dict] = None):
+                  reduce_to_rank0: bool = True, slide_y0: int = 0, slide_h: Optional[int] = None, timings: Optional[dict] = None,
+                  gather: Optional["PeerGather"] = None):
     """Overlapping-tile WSI segmentation (BASELINE.json config 4): T1 tiles -> ESPNet forward + arg-max per
     tile -> T3 max-merge -> T4 /8 mask.  `slide_u8` is the resident BGR slide uint8 [rows,SW,3]: the whole slide, or -- with
     `slide_h` (full height) and `slide_y0` given -- just the rows [slide_y0, slide_y0 + rows) that this rank's band of tiles
     reads (`band_rows`).  With world > 1 the tile rows are sharded across ranks; the forward has no collective; every rank
-    stitches its own band and `gather_bands` places the bands on rank 0.
-    Returns (level0 uint8 [SH,SW] on rank 0 (the rank's band mask [y1-y0,SW] elsewhere, or everywhere when
+    stitches its own band, either straight into rank 0's slide mask over NVLink (`gather` = a PeerGather) or into a local band
+    buffer that `gather_bands` ships to rank 0 (NCCL send / recv).
+    Returns (level0 uint8 [SH,SW] on rank 0 (the rank's band mask [y1-y0,SW] or None elsewhere; the band everywhere when
     reduce_to_rank0=False), ds8 uint8 [int(SH/8), int(SW/8)] on rank 0, n_local_tiles)."""
     if downsample != 1.0:
         raise RuntimeError("only level-0 tiling (downsample 1) is wired to the resident-slide reader")
@@ -272,11 +362,14 @@ def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 51
     row0, rows, y0, y1 = band_rows(grid, sh, rank, world)
     if rows and (slide_y0 > y0 or slide_y0 + int(slide_u8.shape[0]) < y1):
         raise RuntimeError("slide_u8 holds rows [%d,%d) but this rank's tiles read rows [%d,%d)" % (slide_y0, slide_y0 + slide_u8.shape[0], y0, y1))
+    p2p = gather is not None and world > 1 and reduce_to_rank0
+    if p2p and (gather.grid != grid or gather.sh != sh or gather.sw != sw or gather.world != world):
+        raise RuntimeError("the PeerGather was built for another slide / tiling / world size")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
     if ev:
         ev[0].record()
-    band = torch.zeros((y1 - y0, sw), dtype=torch.uint8, device=dev)
     n_local = rows * grid.n_x
+    masks = None
     if n_local:
         org = grid.origins(row0, rows)
         org[:, 1] -= slide_y0                              # tile origins relative to the resident rows
@@ -286,17 +379,23 @@ def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 51
         for s in range(0, n_local, batch):
             e = min(s + batch, n_local)
             model.segment_tiles(slide_u8, origins[s:e], grid.win_y, grid.win_x, mean, std, out=masks[s:e])
-        if ev:
-            ev[1].record()
-        stitch_grid(band, masks, grid, row0, rows, ws, band_y0=y0, slide_h=sh)
-    elif ev:
+    if ev:
         ev[1].record()
+    band = None
+    if not p2p:
+        band = torch.zeros((y1 - y0, sw), dtype=torch.uint8, device=dev)
+        if n_local:
+            stitch_grid(band, masks, grid, row0, rows, ws, band_y0=y0, slide_h=sh)
     if ev:
         ev[2].record()
-    if world > 1 and reduce_to_rank0:
+    if p2p:
+        stats = gather.place(masks, row0, rows, ws)
+        level0 = gather.level0 if rank == 0 else None
+    elif world > 1 and reduce_to_rank0:
         level0, stats = gather_bands(band, grid, sh, sw, rank, world)
+        stats["gather"] = "nccl send/recv"
     else:
-        level0, stats = band, {"bytes_received": 0, "bytes_merged": 0}
+        level0, stats = band, {"bytes_received": 0, "bytes_merged": 0, "gather": "none"}
         if world == 1 and (y0 != 0 or y1 != sh):           # tiles do not reach the last slide rows (cannot happen with T1's ceil)
             level0 = torch.zeros((sh, sw), dtype=torch.uint8, device=dev)
             level0[y0:y1].copy_(band)

@@ -148,10 +148,13 @@ ESPNET_API int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w,
                        const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
                        int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream);
 /* The same into a BAND buffer [band_rows][slide_w] that holds slide rows [band_y0, band_y0 + band_rows): what a rank of a
- * multi-GPU run stitches from its own tile rows without allocating the whole slide mask. */
+ * multi-GPU run stitches from its own tile rows without allocating the whole slide mask.
+ * overwrite = 0: band = max(band, tiles) (zero-initialised or partly filled buffer).  overwrite = 1: every pixel of the rows the
+ * tile rows cover is written (0 where no tile covers it) and nothing is read back: `band_mask` may then be ANOTHER GPU's memory
+ * mapped into this process (CUDA IPC / NVLink P2P) -- the stitch kernel places the band straight into rank 0's slide mask. */
 ESPNET_API int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int slide_h, int slide_w, int y_limit,
                        const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
-                       int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream);
+                       int stride_x, int stride_y, int tile_row0, int tile_rows, int overwrite, void* stream);
 /* dst[i] = max(dst[i], src[i]), n bytes: merge of the rows that two adjacent bands share (the tile-overlap strip) after the
  * band gather; the element-wise max of eval_wsi_segmentation.py:311-312. */
 ESPNET_API int espnet_max_merge_u8(uint8_t* dst, const uint8_t* src, size_t n, void* stream);
