@@ -51,6 +51,7 @@ SYMBOLS = {
     "espnet_stitch_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "espnet_stitch_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
     "espnet_stitch_grid_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
+    "espnet_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
     "espnet_max_merge_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "espnet_ds8_lut": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "espnet_downsample_lut": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -92,6 +92,7 @@ struct espnet_handle {
     std::map<std::string, StageRef> stages;
     int fp32_impl = 1;     // fp32 mode: 1 (default) = tensor cores with 3-term fp16 operand splits (fp32-equivalent), 0 = CUDA-core FMA kernels ("fp32_impl")
     int tc_pair = 0;       // branch stage on tensor cores: 1 = CTA pairs, cta_group::2 M = 256 MMAs (kernels_tc_pair.cuh), 0 = one CTA per tile ("tc_pair")
+    int down_impl = 1;     // tensor-core 3x3-s2 reduce: 1 = TMA-staged input regions (default), 0 = per-thread global loads ("down_impl")
     int tail_impl = 0;     // 1 = run the generic run-time-class-count tail kernels even for 5 / 20 classes ("tail_impl", cross-check)
     int dec_impl = 1;      // decoder tail: 1 = 4 pixels per thread (dec_c4_kernel), 0 = 1 pixel per thread ("dec_impl")
     int l2_reverse = 1;    // 1x1 reduce walks its tiles against the order of the kernel that produced its input (L2 reuse)
@@ -643,15 +644,44 @@ int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
     return ESPNET_OK;
 }
 
+// fp32 tensor map over a planar activation tensor [B][C][H][W] with a {20 cols, 33 rows, 16 channels, 1} box (zero OOB fill):
+// the input region of one K = 16 step of the TMA-staged 3x3-s2 reduce (kernels_tc_down.cuh)
+int make_down_map(espnet_t* h, CUtensorMap* map, const float* in, int B, int C, int H, int W) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kDownBoxCols, (cuuint32_t)kDownRows, 16, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled (3x3-s2 input) failed with CUresult " + std::to_string((int)r));
+    return ESPNET_OK;
+}
+
 template <int CIN, int NOUT, int NKC, bool SPLIT = false>
 int run_reduce3x3_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h, int B, int Hi, int Wi, cudaStream_t st) {
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    const int grid = grid_for(h, (long long)B * ((Ho + 15) / 16) * ((Wo + 7) / 8));
+    const char* name = SPLIT ? (CIN == 19 ? "reduce3x3s2_tc3_l2" : "reduce3x3s2_tc3_l3") : (CIN == 19 ? "reduce3x3s2_tc_l2" : "reduce3x3s2_tc_l3");
+    const __half* wp = reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1));
+    // TMA needs 16 B row pitches and a 16 B aligned base; "down_impl" = 0 forces the per-thread loader kernel (cross-check)
+    if (h->down_impl != 0 && (Wi % 4) == 0 && ((uintptr_t)in % 16) == 0) {
+        using TCfg = DownTmaCfg<CIN, NOUT, SPLIT>;
+        int rc = set_smem(h, reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT>, TCfg::SMEM);
+        if (rc) return rc;
+        CUtensorMap map;
+        rc = make_down_map(h, &map, in, B, CIN, Hi, Wi);
+        if (rc) return rc;
+        { ProfScope _ps(h, name, st); reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, TCfg::SMEM, st>>>(map, wp, o1h, B, Hi, Wi); }
+        LAUNCH_COUNT();
+        CUDA_TRY(h, cudaPeekAtLastError());
+        return ESPNET_OK;
+    }
     using Cfg = DownTcCfg<CIN, NOUT, SPLIT>;
     int rc = set_smem(h, reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT>, Cfg::SMEM);
     if (rc) return rc;
-    const int Ho = Hi / 2, Wo = Wi / 2;
-    const int grid = grid_for(h, (long long)B * ((Ho + 15) / 16) * ((Wo + 7) / 8));
-    { ProfScope _ps(h, SPLIT ? (CIN == 19 ? "reduce3x3s2_tc3_l2" : "reduce3x3s2_tc3_l3") : (CIN == 19 ? "reduce3x3s2_tc_l2" : "reduce3x3s2_tc_l3"), st);
-      reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1)), o1h, B, Hi, Wi); }
+    { ProfScope _ps(h, name, st); reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, Cfg::SMEM, st>>>(in, wp, o1h, B, Hi, Wi); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -983,6 +1013,7 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "fp32_impl") == 0 && value >= 0 && value <= 1) { h->fp32_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "dec_impl") == 0 && value >= 0 && value <= 1) { h->dec_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "down_impl") == 0 && value >= 0 && value <= 1) { h->down_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "tail_impl") == 0 && value >= 0 && value <= 1) { h->tail_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_pair") == 0 && value >= 0 && value <= 1) { h->tc_pair = value; return ESPNET_OK; }
     if (std::strcmp(key, "l2_reverse") == 0 && value >= 0 && value <= 1) { h->l2_reverse = value; return ESPNET_OK; }
@@ -1454,6 +1485,18 @@ int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int 
     if (band_y0 + (long long)band_rows > slide_h) return ESPNET_EINVAL;
     return stitch_grid_launch(band_mask, band_y0, band_rows, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x, win_y, stride_x,
                               stride_y, tile_row0, tile_rows, overwrite != 0, stream);
+}
+
+// Lets kernels running on `device` dereference memory that lives on `peer_device` (NVLink P2P), e.g. rank 0's slide mask that
+// another process mapped through CUDA IPC.  Returns ESPNET_ECUDA when the two GPUs cannot reach each other.
+int espnet_enable_peer_access(int device, int peer_device) {
+    if (device == peer_device) return ESPNET_OK;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, peer_device) != cudaSuccess || !can) { cudaGetLastError(); return ESPNET_ECUDA; }
+    DeviceGuard g(device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return ESPNET_OK; }
+    return e == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
 }
 
 int espnet_max_merge_u8(uint8_t* dst, const uint8_t* src, size_t n, void* stream) {

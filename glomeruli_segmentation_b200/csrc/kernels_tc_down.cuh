@@ -252,4 +252,237 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
     if (warp == 2) tc::tmem_dealloc(tmem_base, 64);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (default when the input row pitch is a multiple of 16 B, i.e. Wi % 4 == 0).
+//
+// The loader warps of the kernel above are INSTRUCTION bound (ncu, profiles/r01_reduce3x3s2_tc3_v1.txt: 14-24 SASS
+// instructions per loaded value -- per-load address arithmetic, image-border and channel-bound tests -- at 0.37-0.40 of the HBM
+// roof).  Here one elected thread hands the whole 33 x 17 region of one K = 16 step to TMA instead: a 4-D tiled load
+// {20 columns (80 B, the next multiple of 16 B), 33 rows, 16 channels, 1 crop} of the planar fp32 input into a shared-memory
+// staging slot.  TMA's out-of-bounds zero fill IS the convolution padding and the channel padding (CIN = 19 / 131 -> 32 /
+// 144), so the loader warps are left with one LDS per value, the fp16 (hi / lo) conversion and one STS.128 per 8 channels
+// into the same parity-split K-major operand stage as above: no global address arithmetic, no bounds tests.
+//   warp 0 = TMA producer of the staging ring, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 = producer of the
+//   streamed split weights, warps 4..11 = converters (staging -> operand stage), warps 12..15 = epilogue.
+constexpr int kDownBoxCols = 20;                                                  // 17 columns padded to a 16 B multiple
+constexpr int kDownStgBytes = 16 * kDownRows * kDownBoxCols * 4;                  // one staging slot: 42240 B
+
+template <int CIN, int NOUT, bool SPLIT = false>
+struct DownTmaCfg {
+    static constexpr int KS = (CIN + 15) / 16;
+    static constexpr int WK = 9 * 2 * NOUT * 16;
+    static constexpr int W_PART = KS * WK;
+    static constexpr int W_RESIDENT = SPLIT ? 0 : W_PART;
+    static constexpr int STAGES = 2;                                             // operand stages
+    static constexpr int SLOTS = 2;                                              // fp32 staging slots
+    static constexpr int STAGE_BYTES = SPLIT ? 2 * kDownStageBytes + 2 * WK : kDownStageBytes;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + W_RESIDENT + (size_t)SLOTS * kDownStgBytes + 256;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    static_assert((STAGES * STAGE_BYTES + W_RESIDENT) % 128 == 0, "TMA destination alignment");
+};
+
+template <int CIN, int NOUT, int NKC, bool SPLIT>
+__global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ w,
+                                                                         __half* __restrict__ o1h, int B, int Hi, int Wi) {
+    using Cfg = DownTmaCfg<CIN, NOUT, SPLIT>;
+    constexpr int KS = Cfg::KS;
+    constexpr int NST = Cfg::STAGES, NSL = Cfg::SLOTS;
+    constexpr int STAGE = Cfg::STAGE_BYTES;
+    static_assert(NKC * 8 == NOUT, "shapes");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* abuf = smem_raw;
+    uint8_t* wbuf = abuf + NST * STAGE;
+    uint8_t* stg = wbuf + Cfg::W_RESIDENT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NSL * kDownStgBytes);
+    uint64_t* a_full = bars + 0;                 // [NST] 8 converter warps (+ the weight producer when SPLIT)
+    uint64_t* a_empty = a_full + NST;            // [NST] MMA commit
+    uint64_t* s_full = a_empty + NST;            // [NSL] TMA transaction bytes
+    uint64_t* s_empty = s_full + NSL;            // [NSL] 8 converter warps
+    uint64_t* acc_full = s_empty + NSL;          // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2] 4 epilogue warps
+    uint64_t* w_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Ho = Hi >> 1, Wo = Wi >> 1;
+    const int tiles_x = (Wo + 7) / 8, tiles_y = (Ho + 15) / 16;
+    const int total_tiles = B * tiles_x * tiles_y;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total = my_tiles * KS;
+
+    if (tid == 0) {
+        if ((tc::smem_addr(stg) & 127u) != 0) __trap();   // TMA destination alignment
+        for (int s = 0; s < NST; ++s) { tc::mbar_init(a_full + s, SPLIT ? 9 : 8); tc::mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < NSL; ++s) { tc::mbar_init(s_full + s, 1); tc::mbar_init(s_empty + s, 8); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 4); }
+        tc::mbar_init(w_full, 1);
+        tc::mbar_fence_init();
+        tc::tma_prefetch_desc(&tmap);
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, 64);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: one 33 x 20 x 16-channel fp32 box per K step into the staging ring =====
+        if (lane == 0) {
+            if constexpr (!SPLIT) {     // resident weights once per CTA
+                tc::mbar_expect_tx(w_full, Cfg::W_PART);
+                tc::bulk_g2s(wbuf, w, Cfg::W_PART, w_full);
+            }
+            int c = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+                const int y_in0 = 2 * (ty * 16) - 1, x_in0 = 2 * (tx * 8) - 1;
+                for (int ks = 0; ks < KS; ++ks, ++c) {
+                    const int sl = c % NSL;
+                    tc::mbar_wait(s_empty + sl, (uint32_t)(((c / NSL) & 1) ^ 1));
+                    tc::mbar_expect_tx(s_full + sl, kDownStgBytes);
+                    tc::tma_load_4d(stg + sl * kDownStgBytes, &tmap, s_full + sl, x_in0, y_in0, 16 * ks, b);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== split mode: hi / lo weights of every K step into its operand stage =====
+        if constexpr (SPLIT) {
+            if (lane == 0) {
+                const uint8_t* wg = reinterpret_cast<const uint8_t*>(w);
+                int c = 0;
+                for (int it = 0; it < my_tiles; ++it)
+                    for (int ks = 0; ks < KS; ++ks, ++c) {
+                        const int s = c % NST;
+                        tc::mbar_wait(a_empty + s, (uint32_t)(((c / NST) & 1) ^ 1));
+                        uint8_t* dst = abuf + s * STAGE + 2 * kDownStageBytes;
+                        tc::mbar_expect_tx(a_full + s, 2 * Cfg::WK);
+                        tc::bulk_g2s(dst, wg + (size_t)ks * Cfg::WK, Cfg::WK, a_full + s);
+                        tc::bulk_g2s(dst + Cfg::WK, wg + (size_t)Cfg::W_PART + (size_t)ks * Cfg::WK, Cfg::WK, a_full + s);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (identical to reduce3x3s2_tc_kernel) =====
+        constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT);
+        constexpr uint32_t a_hi = (uint32_t)((2 * kDownPitch * 16) >> 4) | (1u << 14);   // SBO: next output row = 2 input rows
+        constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+        const uint32_t a_lo0 = (tc::smem_addr(abuf) >> 4) + ((uint32_t)(kDownChunkBytes >> 4) << 16);
+        const uint32_t b_lo0 = (tc::smem_addr(SPLIT ? abuf : wbuf) >> 4) + ((uint32_t)((NOUT * 16) >> 4) << 16);
+        if constexpr (!SPLIT) tc::mbar_wait(w_full, 0);
+        int c = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int as = it & 1;
+            tc::mbar_wait(acc_empty + as, (uint32_t)(((it >> 1) & 1) ^ 1));
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * 32);
+#pragma unroll 1
+            for (int ks = 0; ks < KS; ++ks, ++c) {
+                const int s = c % NST;
+                tc::mbar_wait(a_full + s, (uint32_t)((c / NST) & 1));
+                __syncwarp();
+                tc::tc_fence_after();
+                const uint32_t a_lo_s = a_lo0 + (uint32_t)(s * (STAGE >> 4));
+                const uint32_t b_lo_s = SPLIT ? b_lo0 + (uint32_t)((s * STAGE + 2 * kDownStageBytes) >> 4) : b_lo0 + (uint32_t)(ks * 9 * 2 * NOUT);
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        const uint32_t aoff = (uint32_t)((kx != 1 ? (kDownParBytes >> 4) : 0) + ky * kDownPitch + (kx == 2 ? 1 : 0));
+                        const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + aoff);
+                        const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_s + (uint32_t)(tap * 2 * NOUT));
+                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, (ks | tap) != 0 ? 1u : 0u);
+                        if constexpr (SPLIT) {
+                            tc::umma_f16(d_tmem, adesc + (uint64_t)(kDownStageBytes >> 4), bdesc, idesc, 1u);     // A_lo x W_hi
+                            tc::umma_f16(d_tmem, adesc, bdesc + (uint64_t)(Cfg::WK >> 4), idesc, 1u);            // A_hi x W_lo
+                        }
+                    }
+                    tc::umma_commit(a_empty + s);
+                    if (ks == KS - 1) tc::umma_commit(acc_full + as);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== converters: 256 threads; task t = (K chunk t / 561, region position t % 561): 8 LDS (one per channel of the
+        // chunk, lanes walk region columns), fp16 / split conversion, one STS.128 (two when SPLIT) =====
+        constexpr int POS = kDownRows * kDownCols;             // 561
+        constexpr int TASKS = 2 * POS;
+        constexpr int NT = (TASKS + 255) / 256;                 // 5
+        constexpr int CH_STRIDE = kDownRows * kDownBoxCols;     // floats between channels of the staging box
+        const int lt = tid - 128;
+        int soff[NT], foff[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int t = lt + 256 * i;
+            soff[i] = -1; foff[i] = 0;
+            if (t < TASKS) {
+                const int k = t / POS, pos = t - k * POS;
+                const int r = pos / kDownCols, cc = pos - r * kDownCols;
+                soff[i] = k * kDownChunkBytes + ((cc & 1) ? 0 : kDownParBytes) + (r * kDownPitch + (cc >> 1)) * 16;
+                foff[i] = (8 * k * kDownRows + r) * kDownBoxCols + cc;
+            }
+        }
+#pragma unroll 1
+        for (int c = 0; c < total; ++c) {
+            const int sl = c % NSL, s = c % NST;
+            tc::mbar_wait(s_full + sl, (uint32_t)((c / NSL) & 1));
+            const float* src = reinterpret_cast<const float*>(stg + sl * kDownStgBytes);
+            float v[NT][8];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                if (soff[i] < 0) continue;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[i][j] = src[foff[i] + j * CH_STRIDE];
+            }
+            tc::mbar_wait(a_empty + s, (uint32_t)(((c / NST) & 1) ^ 1));
+            uint8_t* dst = abuf + s * STAGE;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                if (soff[i] < 0) continue;
+                __half2 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if constexpr (SPLIT) split_f16x2(v[i][2 * j], v[i][2 * j + 1], h[j], l[j]);
+                    else h[j] = __floats2half2_rn(v[i][2 * j], v[i][2 * j + 1]);
+                }
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h[0]); u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                u.z = *reinterpret_cast<uint32_t*>(&h[2]); u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                *reinterpret_cast<uint4*>(dst + soff[i]) = u;
+                if constexpr (SPLIT) {
+                    u.x = *reinterpret_cast<uint32_t*>(&l[0]); u.y = *reinterpret_cast<uint32_t*>(&l[1]);
+                    u.z = *reinterpret_cast<uint32_t*>(&l[2]); u.w = *reinterpret_cast<uint32_t*>(&l[3]);
+                    *reinterpret_cast<uint4*>(dst + kDownStageBytes + soff[i]) = u;
+                }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(s_empty + sl); tc::mbar_arrive(a_full + s); }   // the slot's values sit in registers / the stage
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue: TMEM -> fp16 chunk-plane o1h [B][kc][Ho][Wo][8] =====
+        const int q = warp & 3;
+        const int row = 4 * q + (lane >> 3), col = lane & 7;
+        const size_t oplane = (size_t)Ho * Wo;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+            const int y = ty * 16 + row, x = tx * 8 + col;
+            const int as = it & 1;
+            tc::mbar_wait(acc_full + as, (uint32_t)((it >> 1) & 1));
+            tc::tc_fence_after();
+            float v[NOUT];
+            const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * 32);
+            if constexpr (NOUT == 32) tc::tmem_ld32(t0, v); else tc::tmem_ld16(t0, v);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + as);
+            if (y < Ho && x < Wo) store_o1_chunks<NOUT, NKC, SPLIT>(o1h, B, b, oplane, (size_t)y * Wo + x, v);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 64);
+}
+
 }  // namespace espnet

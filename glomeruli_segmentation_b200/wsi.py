@@ -301,13 +301,18 @@ class PeerGather:
             try:
                 if rank != 0:
                     (f0, a0), (f1, a1) = payload
-                    self.level0, self.strips = f0(*a0), f1(*a1)             # cudaIpcOpenMemHandle: rank 0's memory, peer access enabled
-                # every rank proves it can write the peer mapping before the first real use
-                self.strips[rank, 0, :8].fill_(rank + 1)
-                torch.cuda.synchronize(device)
+                    self.level0, self.strips = f0(*a0), f1(*a1)             # cudaIpcOpenMemHandle: rank 0's memory mapped into this process
+                    # the mapping lives in the context of rank 0's GPU; kernels of THIS rank's GPU reach it over NVLink once peer
+                    # access is on (ESPNET_ECUDA if the two GPUs cannot peer)
+                    ok = _lib.lib().espnet_enable_peer_access(device.index, self.level0.device.index) == _lib.OK
             except Exception:
                 ok = False
-            all_ok(ok, "mapping rank 0's slide mask")
+            all_ok(ok, "mapping rank 0's slide mask / enabling peer access")
+            # every rank proves with the stitch kernel itself (running on ITS GPU) that it can write rank 0's memory
+            probe = TileGrid(1, 1, 8, 1, 8, 1)
+            tile = torch.full((1, 1, 8), rank + 1, dtype=torch.uint8, device=device)
+            stitch_grid(self.strips[rank, :1], tile, probe, 0, 1, ws=8, band_y0=0, slide_h=1, overwrite=True)
+            torch.cuda.synchronize(device)
             dist.barrier(group=group)
             ok = True
             if rank == 0:

@@ -99,7 +99,8 @@ ESPNET_API int espnet_set_mode(espnet_t* h, int mode);            /* ESPNET_MODE
  * loads, 2 TMA-staged shared-memory halo tiles); "tc_reduce" (tensor-core modes: 1 = reduce convs on tensor cores, 0 = CUDA
  * cores); "tc_pair" (tensor-core branch stage: 0 = one CTA per MMA tile (default), 1 = clusters of two CTAs with
  * tcgen05 cta_group::2 M = 256 MMAs -- bit-identical results); "l2_reverse" (1x1 reduce walks its tiles against the
- * producer's order to start on the L2-resident part, default 1); "dec_impl" (decoder tail: 1 = 4 pixels per thread); "tail_impl" (1 = generic run-time-class-count tail kernels even for 5 / 20
+ * producer's order to start on the L2-resident part, default 1); "dec_impl" (decoder tail: 1 = 4 pixels per thread); "down_impl" (tensor-core 3x3-s2 reduce: 1 = TMA-staged input regions (default), 0 = per-thread global loads; bit-identical);
+ * "tail_impl" (1 = generic run-time-class-count tail kernels even for 5 / 20
  * classes; bit-identical to the scalar specialised ones). */
 ESPNET_API int espnet_set_option(espnet_t* h, const char* key, int value);
 ESPNET_API size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W);
@@ -155,6 +156,9 @@ ESPNET_API int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w,
 ESPNET_API int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int slide_h, int slide_w, int y_limit,
                        const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
                        int stride_x, int stride_y, int tile_row0, int tile_rows, int overwrite, void* stream);
+/* Enables NVLink peer access device -> peer_device for this process, so that the overwrite form of espnet_stitch_grid_band can
+ * write into a slide mask that lives on peer_device (mapped here through CUDA IPC).  ESPNET_ECUDA if the GPUs cannot peer. */
+ESPNET_API int espnet_enable_peer_access(int device, int peer_device);
 /* dst[i] = max(dst[i], src[i]), n bytes: merge of the rows that two adjacent bands share (the tile-overlap strip) after the
  * band gather; the element-wise max of eval_wsi_segmentation.py:311-312. */
 ESPNET_API int espnet_max_merge_u8(uint8_t* dst, const uint8_t* src, size_t n, void* stream);

@@ -457,4 +457,7 @@ def test_generic_tail_is_bit_identical_to_the_specialised_scalar_tail(fold_sd, n
     ma = a.segment(u8, mean, std, logits=la)
     mb = b.segment(u8, mean, std, logits=lb)
     assert torch.equal(la, lb)
-    assert (ma == mb).float().mean().item() >= (1.0 if net == "full" else 0.9999)
+    if net == "full":
+        assert torch.equal(ma, mb)
+    else:       # the generic x8 up-sampler evaluates the same bilinear formula per pixel instead of per 4-pixel group
+        assert (ma != mb).sum().item() <= 1e-4 * ma.numel()

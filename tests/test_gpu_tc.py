@@ -232,3 +232,22 @@ def test_kernel_variant_options_keep_the_bars(fold_sd, opt, val):
     assert (lg - ref).abs().max().item() <= LOGIT_TOL
     mh = _model(sd, "f16tc").set_option(opt, val).segment(u8, mean, std)
     assert (mh == mref).float().mean().item() >= AGREE
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16tc"])
+@pytest.mark.parametrize("B,H,W", [(2, 512, 512), (3, 264, 328), (1, 72, 40), (2, 136, 200), (1, 8, 8)])
+def test_tma_staged_downsampler_reduce_is_bit_identical(fold_sd, mode, B, H, W):
+    """The TMA-staged 3x3-s2 reduce (option down_impl = 1, default) against the per-thread-loader kernel (down_impl = 0): same
+    operand bytes reach the same MMAs, so every logit must be bit-equal -- including shapes whose level-3 input pitch is not a
+    multiple of 16 B (W/4 % 4 != 0: TMA cannot describe them and the library falls back on its own)."""
+    sd = fold_sd(3)
+    mean, std = FOLD_MEAN_STD[3]
+    u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=H + W, sigma=3.0)).to(DEV)
+    a = _model(sd, mode).set_option("down_impl", 0)
+    b = _model(sd, mode).set_option("down_impl", 1)
+    la, lb = torch.empty((B, 5, H, W), device=DEV), torch.empty((B, 5, H, W), device=DEV)
+    ma = a.segment(u8, mean, std, logits=la)
+    mb = b.segment(u8, mean, std, logits=lb)
+    assert torch.equal(la, lb) and torch.equal(ma, mb)
+    for stage in ("level2_0", "level3_0"):
+        assert torch.equal(a.read_stage(stage), b.read_stage(stage)), stage
