@@ -631,10 +631,13 @@ def measure_wsi(ctx, args, steps, warmup):
     fwd = ctx.max_over_ranks(tm.get("forward_ms", 0.0))
     gather = ctx.max_over_ranks(tm.get("gather_ms", 0.0)) if ctx.world > 1 else 0.0
     clocks = sampler.stop() if ctx.rank == 0 else None
+    hist = torch.bincount(ds8.reshape(-1).long(), minlength=5).tolist() if ctx.rank == 0 else None
+    if gather is not None:
+        del level0, ds8
+        gather.close()
     if ctx.rank != 0:
         return None
     mpx = sw * sh / 1e6
-    hist = torch.bincount(ds8.reshape(-1).long(), minlength=5).tolist()
     return {
         "metric": "WSI Mpx/s", "value": mpx * steps / (ms * 1e-3), "unit": "Mpx/s", "n_gpus": ctx.world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",

@@ -51,7 +51,10 @@ SYMBOLS = {
     "espnet_stitch_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "espnet_stitch_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
     "espnet_stitch_grid_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
-    "espnet_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
+    "espnet_peer_alloc": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]),
+    "espnet_peer_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "espnet_peer_close": (C.c_int, [C.c_void_p, C.c_int]),
+    "espnet_peer_free": (C.c_int, [C.c_void_p, C.c_int]),
     "espnet_max_merge_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "espnet_ds8_lut": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "espnet_downsample_lut": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -646,12 +646,12 @@ int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
 
 // fp32 tensor map over a planar activation tensor [B][C][H][W] with a {20 cols, 33 rows, 16 channels, 1} box (zero OOB fill):
 // the input region of one K = 16 step of the TMA-staged 3x3-s2 reduce (kernels_tc_down.cuh)
-int make_down_map(espnet_t* h, CUtensorMap* map, const float* in, int B, int C, int H, int W) {
+int make_down_map(espnet_t* h, CUtensorMap* map, const float* in, int B, int C, int H, int W, int box_c) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kDownBoxCols, (cuuint32_t)kDownRows, 16, 1};
+    cuuint32_t box[4] = {(cuuint32_t)kDownBoxCols, (cuuint32_t)kDownRows, (cuuint32_t)box_c, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -670,10 +670,12 @@ int run_reduce3x3_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
         using TCfg = DownTmaCfg<CIN, NOUT, SPLIT>;
         int rc = set_smem(h, reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT>, TCfg::SMEM);
         if (rc) return rc;
-        CUtensorMap map;
-        rc = make_down_map(h, &map, in, B, CIN, Hi, Wi);
+        CUtensorMap map, map_tail;
+        rc = make_down_map(h, &map, in, B, CIN, Hi, Wi, 16);
         if (rc) return rc;
-        { ProfScope _ps(h, name, st); reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, TCfg::SMEM, st>>>(map, wp, o1h, B, Hi, Wi); }
+        rc = make_down_map(h, &map_tail, in, B, CIN, Hi, Wi, (CIN % 16) ? (CIN % 16) : 16);     // the last K step's real channels only
+        if (rc) return rc;
+        { ProfScope _ps(h, name, st); reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, TCfg::SMEM, st>>>(map, map_tail, wp, o1h, B, Hi, Wi); }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         return ESPNET_OK;
@@ -1487,16 +1489,48 @@ int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int 
                               stride_y, tile_row0, tile_rows, overwrite != 0, stream);
 }
 
-// Lets kernels running on `device` dereference memory that lives on `peer_device` (NVLink P2P), e.g. rank 0's slide mask that
-// another process mapped through CUDA IPC.  Returns ESPNET_ECUDA when the two GPUs cannot reach each other.
-int espnet_enable_peer_access(int device, int peer_device) {
-    if (device == peer_device) return ESPNET_OK;
-    int can = 0;
-    if (cudaDeviceCanAccessPeer(&can, device, peer_device) != cudaSuccess || !can) { cudaGetLastError(); return ESPNET_ECUDA; }
+// ---- peer-visible buffers (CUDA IPC over NVLink): rank 0 of a multi-GPU run allocates the slide mask here and exports it;
+// the other ranks (processes) map it and their stitch kernels write their bands straight into it (espnet_stitch_grid_band,
+// overwrite form).  The only device memory besides the packed weights that this library ever allocates, and only on request.
+int espnet_peer_alloc(size_t bytes, int device, void** dptr, uint8_t handle64[64]) {
+    if (!dptr || !handle64 || bytes == 0) return ESPNET_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     DeviceGuard g(device);
-    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
-    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return ESPNET_OK; }
-    return e == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return ESPNET_ECUDA; }
+    cudaIpcMemHandle_t hd;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&hd, p) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(p); return ESPNET_ECUDA;
+    }
+    std::memcpy(handle64, &hd, 64);
+    *dptr = p;
+    return ESPNET_OK;
+}
+
+// maps a buffer exported by ANOTHER process for kernels running on `device` (peer access is enabled lazily by the driver)
+int espnet_peer_open(const uint8_t handle64[64], int device, void** dptr) {
+    if (!dptr || !handle64) return ESPNET_EINVAL;
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return ESPNET_ECUDA; }
+    *dptr = p;
+    return ESPNET_OK;
+}
+
+int espnet_peer_close(void* dptr, int device) {
+    if (!dptr) return ESPNET_EINVAL;
+    DeviceGuard g(device);
+    if (cudaIpcCloseMemHandle(dptr) != cudaSuccess) { cudaGetLastError(); return ESPNET_ECUDA; }
+    return ESPNET_OK;
+}
+
+int espnet_peer_free(void* dptr, int device) {
+    if (!dptr) return ESPNET_EINVAL;
+    DeviceGuard g(device);
+    if (cudaFree(dptr) != cudaSuccess) { cudaGetLastError(); return ESPNET_ECUDA; }
+    return ESPNET_OK;
 }
 
 int espnet_max_merge_u8(uint8_t* dst, const uint8_t* src, size_t n, void* stream) {

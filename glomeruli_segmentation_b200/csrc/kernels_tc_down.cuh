@@ -258,13 +258,15 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
 // The loader warps of the kernel above are INSTRUCTION bound (ncu, profiles/r01_reduce3x3s2_tc3_v1.txt: 14-24 SASS
 // instructions per loaded value -- per-load address arithmetic, image-border and channel-bound tests -- at 0.37-0.40 of the HBM
 // roof).  Here one elected thread hands the whole 33 x 17 region of one K = 16 step to TMA instead: a 4-D tiled load
-// {20 columns (80 B, the next multiple of 16 B), 33 rows, 16 channels, 1 crop} of the planar fp32 input into a shared-memory
-// staging slot.  TMA's out-of-bounds zero fill IS the convolution padding and the channel padding (CIN = 19 / 131 -> 32 /
+// {20 columns, 33 rows, 16 channels, 1 crop} of the planar fp32 input into a shared-memory staging slot.  TMA wants the box's
+// innermost start coordinate AND extent on 16 B boundaries (a start at column 2*ox0 - 1 raises "illegal instruction"), so the
+// box starts three columns early, at 2*ox0 - 4, and region column cc is box column cc + 3: 20 columns = exactly 80 B.  TMA's out-of-bounds zero fill IS the convolution padding and the channel padding (CIN = 19 / 131 -> 32 /
 // 144), so the loader warps are left with one LDS per value, the fp16 (hi / lo) conversion and one STS.128 per 8 channels
 // into the same parity-split K-major operand stage as above: no global address arithmetic, no bounds tests.
 //   warp 0 = TMA producer of the staging ring, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 = producer of the
 //   streamed split weights, warps 4..11 = converters (staging -> operand stage), warps 12..15 = epilogue.
-constexpr int kDownBoxCols = 20;                                                  // 17 columns padded to a 16 B multiple
+constexpr int kDownBoxCols = 20;                                                  // columns 2*ox0-4 .. 2*ox0+15: 16 B aligned start and size
+constexpr int kDownBoxSkip = 3;                                                   // region column 0 (= 2*ox0-1) is box column 3
 constexpr int kDownStgBytes = 16 * kDownRows * kDownBoxCols * 4;                  // one staging slot: 42240 B
 
 template <int CIN, int NOUT, bool SPLIT = false>
@@ -282,10 +284,16 @@ struct DownTmaCfg {
 };
 
 template <int CIN, int NOUT, int NKC, bool SPLIT>
-__global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ w,
+__global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                         const __grid_constant__ CUtensorMap tmap_tail, const __half* __restrict__ w,
                                                                          __half* __restrict__ o1h, int B, int Hi, int Wi) {
     using Cfg = DownTmaCfg<CIN, NOUT, SPLIT>;
     constexpr int KS = Cfg::KS;
+    // The TMA engine walks a box row by row and 80 B rows keep it busier than the bytes suggest (~2.4 k cycles per 528-row box,
+    // measured: the chunk period did not change when 13 of the 16 channels of the last K step were out of bounds).  The last K
+    // step only has TAIL = CIN % 16 real channels (3 for both DownSamplers), so it goes through a second map whose box holds
+    // just those: 99 rows instead of 528; the converters fill the missing channels with zeros.
+    constexpr int TAIL = CIN % 16;
     constexpr int NST = Cfg::STAGES, NSL = Cfg::SLOTS;
     constexpr int STAGE = Cfg::STAGE_BYTES;
     static_assert(NKC * 8 == NOUT, "shapes");
@@ -318,6 +326,7 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const 
         tc::mbar_init(w_full, 1);
         tc::mbar_fence_init();
         tc::tma_prefetch_desc(&tmap);
+        if (TAIL) tc::tma_prefetch_desc(&tmap_tail);
     }
     if (warp == 2) tc::tmem_alloc(tmem_slot, 64);
     tc::tc_fence_before();
@@ -336,12 +345,17 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const 
             for (int it = 0; it < my_tiles; ++it) {
                 const int tile = (int)blockIdx.x + it * (int)gridDim.x;
                 const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
-                const int y_in0 = 2 * (ty * 16) - 1, x_in0 = 2 * (tx * 8) - 1;
+                const int y_in0 = 2 * (ty * 16) - 1, x_in0 = 2 * (tx * 8) - 1 - kDownBoxSkip;
                 for (int ks = 0; ks < KS; ++ks, ++c) {
                     const int sl = c % NSL;
                     tc::mbar_wait(s_empty + sl, (uint32_t)(((c / NSL) & 1) ^ 1));
-                    tc::mbar_expect_tx(s_full + sl, kDownStgBytes);
-                    tc::tma_load_4d(stg + sl * kDownStgBytes, &tmap, s_full + sl, x_in0, y_in0, 16 * ks, b);
+                    if (TAIL != 0 && ks == KS - 1) {
+                        tc::mbar_expect_tx(s_full + sl, TAIL * kDownRows * kDownBoxCols * 4);
+                        tc::tma_load_4d(stg + sl * kDownStgBytes, &tmap_tail, s_full + sl, x_in0, y_in0, 16 * ks, b);
+                    } else {
+                        tc::mbar_expect_tx(s_full + sl, kDownStgBytes);
+                        tc::tma_load_4d(stg + sl * kDownStgBytes, &tmap, s_full + sl, x_in0, y_in0, 16 * ks, b);
+                    }
                 }
             }
         }
@@ -410,16 +424,17 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const 
         constexpr int NT = (TASKS + 255) / 256;                 // 5
         constexpr int CH_STRIDE = kDownRows * kDownBoxCols;     // floats between channels of the staging box
         const int lt = tid - 128;
-        int soff[NT], foff[NT];
+        int soff[NT], foff[NT], kk[NT];
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
             const int t = lt + 256 * i;
-            soff[i] = -1; foff[i] = 0;
+            soff[i] = -1; foff[i] = 0; kk[i] = 0;
             if (t < TASKS) {
                 const int k = t / POS, pos = t - k * POS;
+                kk[i] = k;
                 const int r = pos / kDownCols, cc = pos - r * kDownCols;
                 soff[i] = k * kDownChunkBytes + ((cc & 1) ? 0 : kDownParBytes) + (r * kDownPitch + (cc >> 1)) * 16;
-                foff[i] = (8 * k * kDownRows + r) * kDownBoxCols + cc;
+                foff[i] = (8 * k * kDownRows + r) * kDownBoxCols + cc + kDownBoxSkip;
             }
         }
 #pragma unroll 1
@@ -428,11 +443,17 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const 
             tc::mbar_wait(s_full + sl, (uint32_t)((c / NSL) & 1));
             const float* src = reinterpret_cast<const float*>(stg + sl * kDownStgBytes);
             float v[NT][8];
+            const bool tail = TAIL != 0 && (c % KS) == KS - 1;        // warp-uniform: only TAIL channels of this K step were loaded
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
                 if (soff[i] < 0) continue;
+                if (!tail) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[i][j] = src[foff[i] + j * CH_STRIDE];
+                    for (int j = 0; j < 8; ++j) v[i][j] = src[foff[i] + j * CH_STRIDE];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[i][j] = (8 * kk[i] + j < TAIL) ? src[foff[i] + j * CH_STRIDE] : 0.f;
+                }
             }
             tc::mbar_wait(a_empty + s, (uint32_t)(((c / NST) & 1) ^ 1));
             uint8_t* dst = abuf + s * STAGE;

@@ -268,21 +268,41 @@ def band_plan(grid: TileGrid, slide_h: int, world: int):
     return plan
 
 
+class _DeviceBytes:
+    """__cuda_array_interface__ view of raw device memory, so that torch can alias it without owning it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _stitch_raw(out_ptr: int, out_y0: int, out_rows: int, sh: int, sw: int, tile_masks: torch.Tensor, grid: TileGrid, row0: int, rows: int, ws: int):
+    """overwrite-form band stitch into a raw (possibly peer-mapped) pointer; runs on the tiles' device and stream"""
+    dev = tile_masks.device
+    with torch.cuda.device(dev):
+        rc = _lib.lib().espnet_stitch_grid_band(out_ptr, out_y0, out_rows, sh, sw, stitch_y_limit(sw, sh, ws), tile_masks.data_ptr(), grid.n_x,
+                                                grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, row0, rows, 1, _stream(dev))
+    _lib.check(rc, None, "espnet_stitch_grid_band")
+
+
 class PeerGather:
     """Zero-copy band placement over NVLink ("the stitch scatter kernel may write directly into a peer-mapped
     slide buffer, which IS the fused scatter + gather").  Rank 0 allocates the level-0 slide mask and a small staging area for
-    the tile-overlap strips and exports both through CUDA IPC; every other rank maps them and its stitch kernel writes its
-    band's rows straight into rank 0's memory.  Only two tiny barriers and the max-merge of the strips (win - stride rows per
-    rank boundary) remain of the "gather".  Build once per (slide size, tiling, process group) -- the handle exchange is a
-    collective -- and pass to segment_slide(gather=...).  Raises if peer mapping is unavailable; callers then fall back to
-    gather_bands (NCCL send / recv)."""
+    the tile-overlap strips through espnet_peer_alloc and broadcasts their CUDA IPC handles; every other rank (process) maps
+    them with espnet_peer_open and its stitch kernel writes its band's rows straight into rank 0's memory.  Only two tiny
+    barriers and the max-merge of the strips (win - stride rows per rank boundary) remain of the "gather".  Build once per
+    (slide size, tiling, process group) -- the handle exchange is a collective -- and pass to segment_slide(gather=...).
+    Raises (on every rank) if the GPUs cannot peer; callers then fall back to gather_bands (NCCL send / recv)."""
 
     def __init__(self, grid: TileGrid, slide_h: int, slide_w: int, rank: int, world: int, device: torch.device, ws: int = 2400, group=None):
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
         self.grid, self.sh, self.sw, self.rank, self.world, self.group, self.dist = grid, slide_h, slide_w, rank, world, group, dist
+        self.device = device
         self.plan = band_plan(grid, slide_h, world)
-        strip_rows = max([sp - y0 for y0, sp, _ in self.plan] + [1])
+        self.strip_rows = max([sp - y0 for y0, sp, _ in self.plan] + [1])
+        n0, n1 = slide_h * slide_w, world * self.strip_rows * slide_w
+        self._ptr0 = self._ptr1 = None
+        L = _lib.lib()
+
         def all_ok(ok: bool, what: str):
             # failures must be collective: a rank that raised alone would leave the others waiting in the next barrier
             flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
@@ -290,36 +310,58 @@ class PeerGather:
             if int(flag.item()) == 0:
                 raise RuntimeError("PeerGather: %s failed on at least one rank (no CUDA IPC / peer access between the GPUs?)" % what)
 
-        with torch.cuda.device(device):
-            payload = [None, None]
-            if rank == 0:
-                self.level0 = torch.zeros((slide_h, slide_w), dtype=torch.uint8, device=device)       # rows nobody covers stay 0
-                self.strips = torch.zeros((world, strip_rows, slide_w), dtype=torch.uint8, device=device)
-                payload = [reduce_tensor(self.level0), reduce_tensor(self.strips)]
-            dist.broadcast_object_list(payload, src=0, group=group, device=device)
-            ok = True
-            try:
-                if rank != 0:
-                    (f0, a0), (f1, a1) = payload
-                    self.level0, self.strips = f0(*a0), f1(*a1)             # cudaIpcOpenMemHandle: rank 0's memory mapped into this process
-                    # the mapping lives in the context of rank 0's GPU; kernels of THIS rank's GPU reach it over NVLink once peer
-                    # access is on (ESPNET_ECUDA if the two GPUs cannot peer)
-                    ok = _lib.lib().espnet_enable_peer_access(device.index, self.level0.device.index) == _lib.OK
-            except Exception:
-                ok = False
-            all_ok(ok, "mapping rank 0's slide mask / enabling peer access")
-            # every rank proves with the stitch kernel itself (running on ITS GPU) that it can write rank 0's memory
-            probe = TileGrid(1, 1, 8, 1, 8, 1)
-            tile = torch.full((1, 1, 8), rank + 1, dtype=torch.uint8, device=device)
-            stitch_grid(self.strips[rank, :1], tile, probe, 0, 1, ws=8, band_y0=0, slide_h=1, overwrite=True)
+        dev0 = [device.index]
+        dist.broadcast_object_list(dev0, src=0, group=group, device=device)         # which GPU rank 0 sits on
+        all_ok(rank == 0 or (dev0[0] != device.index and torch.cuda.can_device_access_peer(device.index, dev0[0])), "the peer-access capability check")
+        payload = [None, None]
+        ok = True
+        if rank == 0:
+            p0, p1 = C.c_void_p(), C.c_void_p()
+            h0, h1 = C.create_string_buffer(64), C.create_string_buffer(64)
+            ok = L.espnet_peer_alloc(n0, device.index, C.byref(p0), h0) == _lib.OK and L.espnet_peer_alloc(n1, device.index, C.byref(p1), h1) == _lib.OK
+            if ok:
+                self._ptr0, self._ptr1 = p0.value, p1.value
+                payload = [h0.raw, h1.raw]
+        all_ok(ok, "allocating the exported slide mask")
+        dist.broadcast_object_list(payload, src=0, group=group, device=device)
+        ok = True
+        if rank != 0:
+            p0, p1 = C.c_void_p(), C.c_void_p()
+            ok = L.espnet_peer_open(payload[0], device.index, C.byref(p0)) == _lib.OK and L.espnet_peer_open(payload[1], device.index, C.byref(p1)) == _lib.OK
+            if ok:
+                self._ptr0, self._ptr1 = p0.value, p1.value
+        all_ok(ok, "mapping rank 0's slide mask")
+        if rank == 0:       # rank 0 sees its own buffers as ordinary tensors (aliases, not owners)
+            self.level0 = torch.as_tensor(_DeviceBytes(self._ptr0, n0), device=device).view(slide_h, slide_w)
+            self.strips = torch.as_tensor(_DeviceBytes(self._ptr1, n1), device=device).view(world, self.strip_rows, slide_w)
+        # every rank proves with the stitch kernel itself (running on ITS GPU) that it can write rank 0's memory
+        probe = TileGrid(1, 1, 8, 1, 8, 1)
+        tile = torch.full((1, 1, 8), rank + 1, dtype=torch.uint8, device=device)
+        _stitch_raw(self._ptr1 + rank * self.strip_rows * slide_w, 0, 1, 1, slide_w, tile, probe, 0, 1, 8)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+        ok = True
+        if rank == 0:
+            ok = self.strips[:, 0, 0].cpu().tolist() == [r + 1 for r in range(world)]
+            self.strips.zero_()
             torch.cuda.synchronize(device)
-            dist.barrier(group=group)
-            ok = True
-            if rank == 0:
-                ok = self.strips[:, 0, 0].cpu().tolist() == [r + 1 for r in range(world)]
-                self.strips.zero_()
-                torch.cuda.synchronize(device)
-            all_ok(ok, "writing through the peer mapping")
+        all_ok(ok, "writing through the peer mapping")
+
+    def close(self):
+        """Collective: unmap on the peers, then free on rank 0."""
+        if self._ptr0 is None:
+            return
+        L = _lib.lib()
+        torch.cuda.synchronize(self.device)
+        if self.rank != 0:
+            L.espnet_peer_close(self._ptr0, self.device.index)
+            L.espnet_peer_close(self._ptr1, self.device.index)
+        self.dist.barrier(group=self.group)
+        if self.rank == 0:
+            self.level0 = self.strips = None
+            L.espnet_peer_free(self._ptr0, self.device.index)
+            L.espnet_peer_free(self._ptr1, self.device.index)
+        self._ptr0 = self._ptr1 = None
 
     def place(self, tile_masks: Optional[torch.Tensor], row0: int, rows: int, ws: int) -> dict:
         """Collective: every rank stitches its tile rows into rank 0's slide mask (rows it owns) / strip staging (rows shared with
@@ -328,9 +370,9 @@ class PeerGather:
         self.dist.barrier(group=self.group)          # rank 0 is done with the previous result
         if rows and y1 > y0:
             if split > y0:
-                stitch_grid(self.strips[self.rank, :split - y0], tile_masks, self.grid, row0, rows, ws, band_y0=y0, slide_h=self.sh, overwrite=True)
+                _stitch_raw(self._ptr1 + self.rank * self.strip_rows * self.sw, y0, split - y0, self.sh, self.sw, tile_masks, self.grid, row0, rows, ws)
             if y1 > split:
-                stitch_grid(self.level0[split:y1], tile_masks, self.grid, row0, rows, ws, band_y0=split, slide_h=self.sh, overwrite=True)
+                _stitch_raw(self._ptr0 + split * self.sw, split, y1 - split, self.sh, self.sw, tile_masks, self.grid, row0, rows, ws)
         self.dist.barrier(group=self.group)          # every band has landed (kernel completion makes the peer writes visible)
         stats = {"bytes_received": 0, "bytes_merged": 0, "gather": "p2p"}
         if self.rank == 0:

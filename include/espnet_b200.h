@@ -156,9 +156,16 @@ ESPNET_API int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w,
 ESPNET_API int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int slide_h, int slide_w, int y_limit,
                        const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
                        int stride_x, int stride_y, int tile_row0, int tile_rows, int overwrite, void* stream);
-/* Enables NVLink peer access device -> peer_device for this process, so that the overwrite form of espnet_stitch_grid_band can
- * write into a slide mask that lives on peer_device (mapped here through CUDA IPC).  ESPNET_ECUDA if the GPUs cannot peer. */
-ESPNET_API int espnet_enable_peer_access(int device, int peer_device);
+/* Peer-visible buffers for the multi-GPU slide stitch ("the stitch scatter kernel may write directly into a
+ * peer-mapped slide buffer"): espnet_peer_alloc allocates `bytes` of zeroed device memory on `device` and returns its 64-byte
+ * CUDA IPC handle; ANOTHER process maps it with espnet_peer_open for kernels running on ITS `device` (NVLink peer access is
+ * enabled by the driver) and passes the mapped pointer to espnet_stitch_grid_band(..., overwrite = 1).  The owner frees with
+ * espnet_peer_free after every mapper called espnet_peer_close.  The only allocation this library makes besides its packed
+ * weights, and only on request. */
+ESPNET_API int espnet_peer_alloc(size_t bytes, int device, void** dptr, uint8_t handle64[64]);
+ESPNET_API int espnet_peer_open(const uint8_t handle64[64], int device, void** dptr);
+ESPNET_API int espnet_peer_close(void* dptr, int device);
+ESPNET_API int espnet_peer_free(void* dptr, int device);
 /* dst[i] = max(dst[i], src[i]), n bytes: merge of the rows that two adjacent bands share (the tile-overlap strip) after the
  * band gather; the element-wise max of eval_wsi_segmentation.py:311-312. */
 ESPNET_API int espnet_max_merge_u8(uint8_t* dst, const uint8_t* src, size_t n, void* stream);

@@ -51,6 +51,9 @@ def main():
                 ok = bool(torch.equal(level0, ref0)) and bool(torch.equal(ds8, ref8)) and int(n.item()) == n_all == grid.count
                 out.append({"slide": [sw, sh], "overlap": ov, "tiles": grid.count, "mode": mode, "equal_to_single_gpu": ok, "gather": tm})
                 assert ok, out[-1]
+        level0 = ds8 = None
+        if pg is not None:
+            pg.close()
     if rank == 0:
         print(json.dumps({"world": world, "cases": out}))
     dist.destroy_process_group()
