@@ -1451,14 +1451,14 @@ int espnet_stitch_boxes(uint8_t* slide_mask, int slide_h, int slide_w, int y_lim
 }
 
 static int stitch_grid_launch(uint8_t* out, int out_y0, int out_rows, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks, int n_x,
-                              int n_y, int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, int overwrite, void* stream) {
+                              int n_y, int win_x, int win_y, int stride_x, int stride_y, long long k0, long long k1, int overwrite, void* stream) {
     PtrDeviceGuard _dg(tile_masks);      // `out` may be a peer GPU's memory (P2P band placement): launch where the tiles live
     if (!out || !tile_masks || slide_h <= 0 || slide_w <= 0 || n_x <= 0 || n_y <= 0 || win_x <= 0 || win_y <= 0 || stride_x <= 0 ||
-        stride_y <= 0 || tile_row0 < 0 || tile_rows < 0 || tile_row0 + tile_rows > n_y || out_y0 < 0 || out_rows < 0)
+        stride_y <= 0 || k0 < 0 || k1 < k0 || k1 > (long long)n_x * n_y || out_y0 < 0 || out_rows < 0)
         return ESPNET_EINVAL;
-    if (tile_rows == 0 || out_rows == 0) return ESPNET_OK;
-    long long ylo = (long long)tile_row0 * stride_y;
-    long long yhi = (long long)(tile_row0 + tile_rows - 1) * stride_y + win_y;
+    if (k1 == k0 || out_rows == 0) return ESPNET_OK;
+    long long ylo = (k0 / n_x) * stride_y;
+    long long yhi = ((k1 - 1) / n_x) * stride_y + win_y;
     if (yhi > slide_h) yhi = slide_h;
     if (yhi > y_limit) yhi = y_limit;
     if (ylo < out_y0) ylo = out_y0;
@@ -1470,23 +1470,24 @@ static int stitch_grid_launch(uint8_t* out, int out_y0, int out_rows, int slide_
     if (gy > 16384) gy = 16384;          // the kernel strides over the rows: no 65535-row limit on the slide
     dim3 grid(gx, (unsigned)gy);
     stitch_grid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, out_y0, out_rows, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x,
-                                                              win_y, stride_x, stride_y, tile_row0, tile_rows, overwrite);
+                                                              win_y, stride_x, stride_y, (int)k0, (int)k1, overwrite);
     LAUNCH_COUNT();
     return cudaPeekAtLastError() == cudaSuccess ? ESPNET_OK : ESPNET_ECUDA;
 }
 
 int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks, int n_x, int n_y,
                        int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream) {
+    if (tile_row0 < 0 || tile_rows < 0 || tile_row0 + tile_rows > n_y) return ESPNET_EINVAL;
     return stitch_grid_launch(slide_mask, 0, slide_h, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x, win_y, stride_x, stride_y,
-                              tile_row0, tile_rows, 0, stream);
+                              (long long)tile_row0 * n_x, (long long)(tile_row0 + tile_rows) * n_x, 0, stream);
 }
 
 int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int slide_h, int slide_w, int y_limit, const uint8_t* tile_masks,
-                            int n_x, int n_y, int win_x, int win_y, int stride_x, int stride_y, int tile_row0, int tile_rows, int overwrite,
+                            int n_x, int n_y, int win_x, int win_y, int stride_x, int stride_y, int tile_k0, int tile_k1, int overwrite,
                             void* stream) {
     if (band_y0 + (long long)band_rows > slide_h) return ESPNET_EINVAL;
     return stitch_grid_launch(band_mask, band_y0, band_rows, slide_h, slide_w, y_limit, tile_masks, n_x, n_y, win_x, win_y, stride_x,
-                              stride_y, tile_row0, tile_rows, overwrite != 0, stream);
+                              stride_y, tile_k0, tile_k1, overwrite != 0, stream);
 }
 
 // ---- peer-visible buffers (CUDA IPC over NVLink): rank 0 of a multi-GPU run allocates the slide mask here and exports it;

@@ -80,12 +80,15 @@ __global__ void stitch_boxes_tail_kernel(unsigned char* __restrict__ slide, int 
 // `out` is another GPU's memory mapped over NVLink (P2P band placement: a remote read-modify-write would cost a round trip).
 __global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restrict__ out, int out_y0, int out_rows, int SH, int SW, int y_limit,
                                                           const unsigned char* __restrict__ tiles, int n_x, int n_y,
-                                                          int win_x, int win_y, int sx, int sy, int row0, int rows, int overwrite) {
+                                                          int win_x, int win_y, int sx, int sy, int k0, int k1, int overwrite) {
+    // resident tiles: indices [k0, k1) of the row-major grid (a rank's share; whole tile rows or a balanced range that starts /
+    // ends inside a row); tile k sits at tiles + (k - k0) * win_x * win_y
+    const int row0 = k0 / n_x, row1 = (k1 - 1) / n_x;
     const int ylo = max(row0 * sy, out_y0);
-    const int yhi = min(min(min((row0 + rows - 1) * sy + win_y, SH), y_limit), out_y0 + out_rows);
+    const int yhi = min(min(min(row1 * sy + win_y, SH), y_limit), out_y0 + out_rows);
     const size_t tile_sz = (size_t)win_x * win_y;
     for (int y = ylo + blockIdx.y; y < yhi; y += gridDim.y) {
-        const int j_hi = min(min(y / sy, n_y - 1), row0 + rows - 1);
+        const int j_hi = min(min(y / sy, n_y - 1), row1);
         int j_lo = (y - win_y + sy) / sy;                 // ceil((y - win_y + 1) / sy) for y-win_y+1 > 0
         if (y - win_y + 1 <= 0) j_lo = 0;
         j_lo = max(j_lo, row0);
@@ -99,8 +102,9 @@ __global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restr
                 if (ty < 0 || ty >= win_y) continue;
                 for (int i = i_lo; i <= i_hi; ++i) {
                     const int tx = x - i * sx;
-                    if (tx < 0 || tx >= win_x) continue;
-                    const int v = tiles[((size_t)(j - row0) * n_x + i) * tile_sz + (size_t)ty * win_x + tx];
+                    const int k = j * n_x + i;
+                    if (tx < 0 || tx >= win_x || k < k0 || k >= k1) continue;
+                    const int v = tiles[(size_t)(k - k0) * tile_sz + (size_t)ty * win_x + tx];
                     best = max(best, v);
                 }
             }

@@ -45,6 +45,11 @@ class TileGrid:
         jj, ii = np.meshgrid(np.arange(row0, row0 + rows), np.arange(self.n_x), indexing="ij")
         return np.stack([ii.reshape(-1) * self.stride_x, jj.reshape(-1) * self.stride_y], 1).astype(np.int32)
 
+    def origins_range(self, k0: int, k1: int) -> np.ndarray:
+        """(x_start, y_start) int32 of the tiles with row-major index k0 <= k < k1 (k = j * n_x + i, scan_region's order)."""
+        k = np.arange(k0, k1)
+        return np.stack([(k % self.n_x) * self.stride_x, (k // self.n_x) * self.stride_y], 1).astype(np.int32)
+
 
 def tile_grid(slide_w: int, slide_h: int, std_size: float = 512, mpp_x: float = 1.0, mpp_y: float = 1.0,
               overlap: float = 0.1, downsample: float = 1.0) -> TileGrid:
@@ -92,7 +97,7 @@ def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def band_rows(grid: TileGrid, slide_h: int, rank: int, world: int) -> Tuple[int, int, int, int]:
-    """(tile_row0, tile_rows, y0, y1): the tile rows of `rank` and the slide rows [y0, y1) their tiles cover
+    """(tile_row0, tile_rows, y0, y1): whole tile rows for `rank` and the slide rows [y0, y1) their tiles cover
     (clipped to the slide).  Adjacent bands share win_y - stride_y rows (the tile overlap)."""
     row0, rows = shard_rows(grid.n_y, rank, world)
     if rows == 0:
@@ -100,6 +105,24 @@ def band_rows(grid: TileGrid, slide_h: int, rank: int, world: int) -> Tuple[int,
     y0 = row0 * grid.stride_y
     y1 = min(slide_h, (row0 + rows - 1) * grid.stride_y + grid.win_y)
     return row0, rows, min(y0, slide_h), max(y1, min(y0, slide_h))
+
+
+def band_tiles(grid: TileGrid, slide_h: int, rank: int, world: int, balance: str = "tiles") -> Tuple[int, int, int, int]:
+    """(k0, k1, y0, y1): the row-major tile index range of `rank` and the slide rows [y0, y1) those tiles touch.
+    balance="tiles" (default) splits the TILES evenly -- a range may start / end inside a tile row, the two neighbours then both
+    touch that row's slide rows and the stitch merges them; balance="rows" hands out whole tile rows (band_rows)."""
+    if balance == "rows":
+        row0, rows, y0, y1 = band_rows(grid, slide_h, rank, world)
+        return row0 * grid.n_x, (row0 + rows) * grid.n_x, y0, y1
+    if balance != "tiles":
+        raise ValueError(balance)
+    k0, n = shard_rows(grid.count, rank, world)        # the same contiguous split, over tiles instead of rows
+    k1 = k0 + n
+    if n == 0:
+        return k0, k1, 0, 0
+    y0 = min((k0 // grid.n_x) * grid.stride_y, slide_h)
+    y1 = min(slide_h, ((k1 - 1) // grid.n_x) * grid.stride_y + grid.win_y)
+    return k0, k1, y0, max(y1, y0)
 
 
 def _stream(dev) -> int:
@@ -141,21 +164,22 @@ def stitch_boxes(slide_mask: torch.Tensor, boxes: Sequence[Sequence[float]], mas
 
 
 def stitch_grid(slide_mask: torch.Tensor, tile_masks: torch.Tensor, grid: TileGrid, row0: int, rows: int, ws: int = 2400,
-                band_y0: int = 0, slide_h: Optional[int] = None, overwrite: bool = False):
-    """T3 for the regular tile grid, gather form.  tile_masks: uint8 [rows*n_x, win_y, win_x].  `slide_mask` is the whole
-    level-0 mask [SH,SW] (default) or, with `slide_h` given, a band buffer holding slide rows [band_y0, band_y0 + its height).
-    overwrite=True writes every pixel of the covered rows without reading the destination, which may then live on ANOTHER GPU
-    (a CUDA-IPC mapping of rank 0's slide mask: the stitch kernel places the band over NVLink, see PeerGather)."""
+                band_y0: int = 0, slide_h: Optional[int] = None, overwrite: bool = False, tiles: Optional[Tuple[int, int]] = None):
+    """T3 for the regular tile grid, gather form.  tile_masks: uint8 [n, win_y, win_x] = the tiles of rows [row0, row0 + rows)
+    or, with tiles=(k0, k1), the row-major tile index range [k0, k1).  `slide_mask` is the whole level-0 mask [SH,SW] (default)
+    or, with `slide_h` given, a band buffer holding slide rows [band_y0, band_y0 + its height).
+    overwrite=True writes every pixel of the covered rows without reading the destination."""
+    k0, k1 = tiles if tiles is not None else (row0 * grid.n_x, (row0 + rows) * grid.n_x)
     _check_u8(slide_mask, "slide_mask", 2)
     _check_u8(tile_masks, "tile_masks", 3, None if overwrite else slide_mask.device)
-    if tuple(tile_masks.shape) != (rows * grid.n_x, grid.win_y, grid.win_x):
-        raise RuntimeError("tile_masks must be [rows*n_x, win_y, win_x] = %s, got %s" % ((rows * grid.n_x, grid.win_y, grid.win_x), tuple(tile_masks.shape)))
+    if tuple(tile_masks.shape) != (k1 - k0, grid.win_y, grid.win_x):
+        raise RuntimeError("tile_masks must be [n_tiles, win_y, win_x] = %s, got %s" % ((k1 - k0, grid.win_y, grid.win_x), tuple(tile_masks.shape)))
     bh, sw = slide_mask.shape
     sh = bh if slide_h is None else int(slide_h)
     dev = tile_masks.device                    # the kernel runs where the tiles are
     with torch.cuda.device(dev):
         rc = _lib.lib().espnet_stitch_grid_band(slide_mask.data_ptr(), band_y0, bh, sh, sw, stitch_y_limit(sw, sh, ws), tile_masks.data_ptr(),
-                                                grid.n_x, grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, row0, rows,
+                                                grid.n_x, grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, k0, k1,
                                                 int(overwrite), _stream(dev))
     _lib.check(rc, None, "espnet_stitch_grid_band")
     return slide_mask
@@ -201,7 +225,7 @@ def downsample8(level0: torch.Tensor, ws: int = 2400) -> torch.Tensor:
 
 
 def gather_bands(band: Optional[torch.Tensor], grid: TileGrid, slide_h: int, slide_w: int, rank: int, world: int,
-                 merge=None, group=None) -> Tuple[Optional[torch.Tensor], dict]:
+                 merge=None, group=None, balance: str = "tiles") -> Tuple[Optional[torch.Tensor], dict]:
     """The one exchange of the multi-GPU WSI path: every rank hands its band mask (slide rows
     [y0_r, y1_r), `band_rows`) to rank 0.  Rank 0 allocates the level-0 mask, keeps its own band, receives the rows no earlier
     band covers STRAIGHT INTO their place in the slide mask, and only the rows a band shares with its predecessors (the tile
@@ -209,7 +233,8 @@ def gather_bands(band: Optional[torch.Tensor], grid: TileGrid, slide_h: int, sli
     (NCCL send/recv over NVLink, grouped), no reduction over the whole mask.  Returns (level0 on rank 0 else None, stats)."""
     import torch.distributed as dist
     merge = merge or (lambda d, s: max_merge_(d, s))
-    bands = [band_rows(grid, slide_h, r, world) for r in range(world)]
+    bands = [band_tiles(grid, slide_h, r, world, balance) for r in range(world)]
+    bands = [(k0, k1 - k0, y0, y1) for k0, k1, y0, y1 in bands]          # (first tile, tile count, y0, y1)
     stats = {"bytes_received": 0, "bytes_merged": 0}
     if rank != 0:
         _, rows, y0, y1 = bands[rank]
@@ -253,13 +278,13 @@ def gather_bands(band: Optional[torch.Tensor], grid: TileGrid, slide_h: int, sli
     return level0, stats
 
 
-def band_plan(grid: TileGrid, slide_h: int, world: int):
-    """Per rank (y0, split, y1): band rows [y0, y1); rows [y0, split) are also covered by an earlier rank's band (they need the
+def band_plan(grid: TileGrid, slide_h: int, world: int, balance: str = "tiles"):
+    """Per rank (y0, split, y1): band rows [y0, y1); rows [y0, split) are also touched by an earlier rank's band (they need the
     max-merge), rows [split, y1) are this rank's to place."""
     plan, cov = [], 0
     for r in range(world):
-        _, rows, y0, y1 = band_rows(grid, slide_h, r, world)
-        if not rows or y1 <= y0:
+        k0, k1, y0, y1 = band_tiles(grid, slide_h, r, world, balance)
+        if k1 <= k0 or y1 <= y0:
             plan.append((0, 0, 0))
             continue
         split = min(max(cov, y0), y1)
@@ -275,12 +300,12 @@ class _DeviceBytes:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def _stitch_raw(out_ptr: int, out_y0: int, out_rows: int, sh: int, sw: int, tile_masks: torch.Tensor, grid: TileGrid, row0: int, rows: int, ws: int):
-    """overwrite-form band stitch into a raw (possibly peer-mapped) pointer; runs on the tiles' device and stream"""
+def _stitch_raw(out_ptr: int, out_y0: int, out_rows: int, sh: int, sw: int, tile_masks: torch.Tensor, grid: TileGrid, k0: int, k1: int, ws: int):
+    """overwrite-form band stitch of tiles [k0, k1) into a raw (possibly peer-mapped) pointer; runs on the tiles' device and stream"""
     dev = tile_masks.device
     with torch.cuda.device(dev):
         rc = _lib.lib().espnet_stitch_grid_band(out_ptr, out_y0, out_rows, sh, sw, stitch_y_limit(sw, sh, ws), tile_masks.data_ptr(), grid.n_x,
-                                                grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, row0, rows, 1, _stream(dev))
+                                                grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y, k0, k1, 1, _stream(dev))
     _lib.check(rc, None, "espnet_stitch_grid_band")
 
 
@@ -293,11 +318,12 @@ class PeerGather:
     (slide size, tiling, process group) -- the handle exchange is a collective -- and pass to segment_slide(gather=...).
     Raises (on every rank) if the GPUs cannot peer; callers then fall back to gather_bands (NCCL send / recv)."""
 
-    def __init__(self, grid: TileGrid, slide_h: int, slide_w: int, rank: int, world: int, device: torch.device, ws: int = 2400, group=None):
+    def __init__(self, grid: TileGrid, slide_h: int, slide_w: int, rank: int, world: int, device: torch.device, ws: int = 2400, group=None,
+                 balance: str = "tiles"):
         import torch.distributed as dist
         self.grid, self.sh, self.sw, self.rank, self.world, self.group, self.dist = grid, slide_h, slide_w, rank, world, group, dist
-        self.device = device
-        self.plan = band_plan(grid, slide_h, world)
+        self.device, self.balance = device, balance
+        self.plan = band_plan(grid, slide_h, world, balance)
         self.strip_rows = max([sp - y0 for y0, sp, _ in self.plan] + [1])
         n0, n1 = slide_h * slide_w, world * self.strip_rows * slide_w
         self._ptr0 = self._ptr1 = None
@@ -363,16 +389,16 @@ class PeerGather:
             L.espnet_peer_free(self._ptr1, self.device.index)
         self._ptr0 = self._ptr1 = None
 
-    def place(self, tile_masks: Optional[torch.Tensor], row0: int, rows: int, ws: int) -> dict:
-        """Collective: every rank stitches its tile rows into rank 0's slide mask (rows it owns) / strip staging (rows shared with
-        an earlier band); rank 0 merges the strips.  Returns byte counts."""
+    def place(self, tile_masks: Optional[torch.Tensor], k0: int, k1: int, ws: int) -> dict:
+        """Collective: every rank stitches its tiles [k0, k1) into rank 0's slide mask (rows it owns) / strip staging (rows shared
+        with an earlier band); rank 0 merges the strips.  Returns byte counts."""
         y0, split, y1 = self.plan[self.rank]
         self.dist.barrier(group=self.group)          # rank 0 is done with the previous result
-        if rows and y1 > y0:
+        if k1 > k0 and y1 > y0:
             if split > y0:
-                _stitch_raw(self._ptr1 + self.rank * self.strip_rows * self.sw, y0, split - y0, self.sh, self.sw, tile_masks, self.grid, row0, rows, ws)
+                _stitch_raw(self._ptr1 + self.rank * self.strip_rows * self.sw, y0, split - y0, self.sh, self.sw, tile_masks, self.grid, k0, k1, ws)
             if y1 > split:
-                _stitch_raw(self._ptr0 + split * self.sw, split, y1 - split, self.sh, self.sw, tile_masks, self.grid, row0, rows, ws)
+                _stitch_raw(self._ptr0 + split * self.sw, split, y1 - split, self.sh, self.sw, tile_masks, self.grid, k0, k1, ws)
         self.dist.barrier(group=self.group)          # every band has landed (kernel completion makes the peer writes visible)
         stats = {"bytes_received": 0, "bytes_merged": 0, "gather": "p2p"}
         if self.rank == 0:
@@ -388,13 +414,14 @@ class PeerGather:
 def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 512, mpp: float = 1.0, overlap: float = 0.1,
                   downsample: float = 1.0, ws: int = 2400, batch: int = 256, rank: int = 0, world: int = 1,
                   reduce_to_rank0: bool = True, slide_y0: int = 0, slide_h: Optional[int] = None, timings: Optional[dict] = None,
-                  gather: Optional["PeerGather"] = None):
+                  gather: Optional["PeerGather"] = None, balance: str = "tiles"):
     """Overlapping-tile WSI segmentation (BASELINE.json config 4): T1 tiles -> ESPNet forward + arg-max per
     tile -> T3 max-merge -> T4 /8 mask.  `slide_u8` is the resident BGR slide uint8 [rows,SW,3]: the whole slide, or -- with
-    `slide_h` (full height) and `slide_y0` given -- just the rows [slide_y0, slide_y0 + rows) that this rank's band of tiles
-    reads (`band_rows`).  With world > 1 the tile rows are sharded across ranks; the forward has no collective; every rank
-    stitches its own band, either straight into rank 0's slide mask over NVLink (`gather` = a PeerGather) or into a local band
-    buffer that `gather_bands` ships to rank 0 (NCCL send / recv).
+    `slide_h` (full height) and `slide_y0` given -- just the rows [slide_y0, slide_y0 + rows) that this rank's tiles read
+    (`band_tiles`).  With world > 1 the tiles are sharded across ranks as contiguous, equally sized ranges of scan_region's
+    row-major order (balance="tiles"; "rows" hands out whole tile rows); the forward has no collective; every rank stitches its
+    own band, either straight into rank 0's slide mask over NVLink (`gather` = a PeerGather) or into a local band buffer that
+    `gather_bands` ships to rank 0 (NCCL send / recv).
     Returns (level0 uint8 [SH,SW] on rank 0 (the rank's band mask [y1-y0,SW] or None elsewhere; the band everywhere when
     reduce_to_rank0=False), ds8 uint8 [int(SH/8), int(SW/8)] on rank 0, n_local_tiles)."""
     if downsample != 1.0:
@@ -406,19 +433,19 @@ def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 51
     grid = tile_grid(sw, sh, std_size, mpp, mpp, overlap, downsample)
     if grid.win_x % 8 or grid.win_y % 8:
         raise RuntimeError("tile size %dx%d is not a multiple of 8 (ESPNet needs it, Model.py cat at :373)" % (grid.win_x, grid.win_y))
-    row0, rows, y0, y1 = band_rows(grid, sh, rank, world)
-    if rows and (slide_y0 > y0 or slide_y0 + int(slide_u8.shape[0]) < y1):
+    k0, k1, y0, y1 = band_tiles(grid, sh, rank, world, balance)
+    n_local = k1 - k0
+    if n_local and (slide_y0 > y0 or slide_y0 + int(slide_u8.shape[0]) < y1):
         raise RuntimeError("slide_u8 holds rows [%d,%d) but this rank's tiles read rows [%d,%d)" % (slide_y0, slide_y0 + slide_u8.shape[0], y0, y1))
     p2p = gather is not None and world > 1 and reduce_to_rank0
-    if p2p and (gather.grid != grid or gather.sh != sh or gather.sw != sw or gather.world != world):
-        raise RuntimeError("the PeerGather was built for another slide / tiling / world size")
+    if p2p and (gather.grid != grid or gather.sh != sh or gather.sw != sw or gather.world != world or gather.balance != balance):
+        raise RuntimeError("the PeerGather was built for another slide / tiling / world size / balance")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
     if ev:
         ev[0].record()
-    n_local = rows * grid.n_x
     masks = None
     if n_local:
-        org = grid.origins(row0, rows)
+        org = grid.origins_range(k0, k1)
         org[:, 1] -= slide_y0                              # tile origins relative to the resident rows
         origins = torch.from_numpy(org).to(dev)
         masks = torch.empty((n_local, grid.win_y, grid.win_x), dtype=torch.uint8, device=dev)
@@ -432,14 +459,14 @@ def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 51
     if not p2p:
         band = torch.zeros((y1 - y0, sw), dtype=torch.uint8, device=dev)
         if n_local:
-            stitch_grid(band, masks, grid, row0, rows, ws, band_y0=y0, slide_h=sh)
+            stitch_grid(band, masks, grid, 0, 0, ws, band_y0=y0, slide_h=sh, tiles=(k0, k1))
     if ev:
         ev[2].record()
     if p2p:
-        stats = gather.place(masks, row0, rows, ws)
+        stats = gather.place(masks, k0, k1, ws)
         level0 = gather.level0 if rank == 0 else None
     elif world > 1 and reduce_to_rank0:
-        level0, stats = gather_bands(band, grid, sh, sw, rank, world)
+        level0, stats = gather_bands(band, grid, sh, sw, rank, world, balance=balance)
         stats["gather"] = "nccl send/recv"
     else:
         level0, stats = band, {"bytes_received": 0, "bytes_merged": 0, "gather": "none"}

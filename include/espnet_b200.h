@@ -149,13 +149,15 @@ ESPNET_API int espnet_stitch_grid(uint8_t* slide_mask, int slide_h, int slide_w,
                        const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
                        int stride_x, int stride_y, int tile_row0, int tile_rows, void* stream);
 /* The same into a BAND buffer [band_rows][slide_w] that holds slide rows [band_y0, band_y0 + band_rows): what a rank of a
- * multi-GPU run stitches from its own tile rows without allocating the whole slide mask.
+ * multi-GPU run stitches from its own tiles without allocating the whole slide mask.  The rank's tiles are the
+ * row-major index range [tile_k0, tile_k1) of the T1 grid (whole tile rows, or a balanced share that starts / ends inside a row);
+ * tile_masks holds exactly those, tile k at (k - tile_k0) * win_x * win_y.
  * overwrite = 0: band = max(band, tiles) (zero-initialised or partly filled buffer).  overwrite = 1: every pixel of the rows the
- * tile rows cover is written (0 where no tile covers it) and nothing is read back: `band_mask` may then be ANOTHER GPU's memory
- * mapped into this process (CUDA IPC / NVLink P2P) -- the stitch kernel places the band straight into rank 0's slide mask. */
+ * tiles' rows cover is written (0 where no resident tile covers it) and nothing is read back: `band_mask` may then be ANOTHER
+ * GPU's memory mapped into this process (espnet_peer_open) -- the stitch kernel places the band straight into rank 0's slide mask. */
 ESPNET_API int espnet_stitch_grid_band(uint8_t* band_mask, int band_y0, int band_rows, int slide_h, int slide_w, int y_limit,
                        const uint8_t* tile_masks, int n_x, int n_y, int win_x, int win_y,
-                       int stride_x, int stride_y, int tile_row0, int tile_rows, int overwrite, void* stream);
+                       int stride_x, int stride_y, int tile_k0, int tile_k1, int overwrite, void* stream);
 /* Peer-visible buffers for the multi-GPU slide stitch ("the stitch scatter kernel may write directly into a
  * peer-mapped slide buffer"): espnet_peer_alloc allocates `bytes` of zeroed device memory on `device` and returns its 64-byte
  * CUDA IPC handle; ANOTHER process maps it with espnet_peer_open for kernels running on ITS `device` (NVLink peer access is

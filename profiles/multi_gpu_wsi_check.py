@@ -28,7 +28,7 @@ def main():
     out = []
     for (sw, sh, ov) in ((4096, 3072, 0.1), (3000, 5000, 0.5), (1500, 1100, 0.25)):
         grid = wsi.tile_grid(sw, sh, 512, 1.0, 1.0, ov, 1.0)
-        row0, rows, y0, y1 = wsi.band_rows(grid, sh, rank, world)
+        k0, k1, y0, y1 = wsi.band_tiles(grid, sh, rank, world)
         band_slide = bench.synth_slide_rows(dev, sw, y0, y1, seed=7, block=512)
         whole = bench.synth_slide_rows(dev, sw, 0, sh, seed=7, block=512) if rank == 0 else None
         ref = wsi.segment_slide(model, whole, mean, std, overlap=ov, batch=64) if rank == 0 else None

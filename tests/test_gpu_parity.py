@@ -313,18 +313,24 @@ def test_band_buffers_and_overlap_merge_equal_the_single_pass():
     full = torch.zeros((sh, sw), dtype=torch.uint8, device=DEV)
     wsi.stitch_grid(full, d_tiles, grid, 0, grid.n_y, ws)
     assert np.array_equal(full.cpu().numpy(), _cpu_grid_stitch(sw, sh, grid, tiles, 0, grid.n_y, wsi.stitch_y_limit(sw, sh, ws)))
-    out = torch.zeros_like(full)
-    cov = 0
-    for r in range(3):
-        row0, rows, y0, y1 = wsi.band_rows(grid, sh, r, 3)
-        band = torch.zeros((y1 - y0, sw), dtype=torch.uint8, device=DEV)
-        wsi.stitch_grid(band, d_tiles[row0 * grid.n_x:(row0 + rows) * grid.n_x], grid, row0, rows, ws, band_y0=y0, slide_h=sh)
-        split = min(max(cov, y0), y1)
-        if split > y0:
-            wsi.max_merge_(out[y0:split], band[:split - y0].contiguous())
-        out[split:y1].copy_(band[split - y0:])
-        cov = max(cov, y1)
-    assert torch.equal(out, full)
+    for balance in ("rows", "tiles"):
+        out = torch.zeros_like(full)
+        cov = 0
+        for r in range(3):
+            k0, k1, y0, y1 = wsi.band_tiles(grid, sh, r, 3, balance)
+            band = torch.zeros((y1 - y0, sw), dtype=torch.uint8, device=DEV)
+            wsi.stitch_grid(band, d_tiles[k0:k1], grid, 0, 0, ws, band_y0=y0, slide_h=sh, tiles=(k0, k1))
+            # overwrite form into a dirty buffer: every pixel of the band's rows is written, nothing read
+            dirty = torch.full_like(band, 9)
+            wsi.stitch_grid(dirty, d_tiles[k0:k1], grid, 0, 0, ws, band_y0=y0, slide_h=sh, tiles=(k0, k1), overwrite=True)
+            lim = wsi.stitch_y_limit(sw, sh, ws)
+            assert torch.equal(dirty[:max(0, min(lim, y1) - y0)], band[:max(0, min(lim, y1) - y0)])
+            split = min(max(cov, y0), y1)
+            if split > y0:
+                wsi.max_merge_(out[y0:split], band[:split - y0].contiguous())
+            out[split:y1].copy_(band[split - y0:])
+            cov = max(cov, y1)
+        assert torch.equal(out, full), balance
     # unaligned / odd-length merge goes through the byte path
     a = torch.randint(0, 5, (1001,), dtype=torch.uint8, device=DEV)
     b = torch.randint(0, 5, (1001,), dtype=torch.uint8, device=DEV)

@@ -46,18 +46,29 @@ def _band_mask(sw, sh, grid, row0, rows, y_limit):
     return out
 
 
-def _worker(rank, world, port, sw, sh, ov, q):
+def _range_mask(sw, sh, grid, k0, k1, y_limit):
+    """The same for a row-major tile index range [k0, k1) (balance="tiles")."""
+    out = np.zeros((sh, sw), np.uint8)
+    for k, (x0, y0) in zip(range(k0, k1), grid.origins_range(k0, k1)):
+        m = _tile_mask(k, grid.win_y, grid.win_x)
+        x1, y1 = min(x0 + grid.win_x, sw), min(min(y0 + grid.win_y, sh), y_limit)
+        if x1 > x0 and y1 > y0:
+            out[y0:y1, x0:x1] = np.maximum(out[y0:y1, x0:x1], m[: y1 - y0, : x1 - x0])
+    return out
+
+
+def _worker(rank, world, port, sw, sh, ov, q, balance="rows"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         grid = wsi.tile_grid(sw, sh, 64, 1.0, 1.0, ov, 1.0)
-        row0, rows, y0, y1 = wsi.band_rows(grid, sh, rank, world)
+        k0, k1, y0, y1 = wsi.band_tiles(grid, sh, rank, world, balance)
         ylim = wsi.stitch_y_limit(sw, sh, 2400)
         # the rank's band buffer holds ONLY slide rows [y0, y1)
-        band = torch.from_numpy(_band_mask(sw, sh, grid, row0, rows, ylim)[y0:y1].copy())
-        level0, stats = wsi.gather_bands(band, grid, sh, sw, rank, world, merge=lambda d, s: d.copy_(torch.maximum(d, s)))
-        counts = torch.tensor([rows * grid.n_x], dtype=torch.int64)
+        band = torch.from_numpy(_range_mask(sw, sh, grid, k0, k1, ylim)[y0:y1].copy())
+        level0, stats = wsi.gather_bands(band, grid, sh, sw, rank, world, merge=lambda d, s: d.copy_(torch.maximum(d, s)), balance=balance)
+        counts = torch.tensor([k1 - k0], dtype=torch.int64)
         dist.all_reduce(counts)
         if rank == 0:
             q.put((level0.numpy(), int(counts.item()), stats))
@@ -67,12 +78,13 @@ def _worker(rank, world, port, sw, sh, ov, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("sw,sh,ov,world", [(500, 380, 0.1, 2), (333, 420, 0.5, 2), (300, 700, 0.5, 3), (200, 130, 0.1, 3)])
-def test_band_sharding_and_gather_equal_single_process(sw, sh, ov, world):
+@pytest.mark.parametrize("sw,sh,ov,world,balance", [(500, 380, 0.1, 2, "rows"), (333, 420, 0.5, 2, "tiles"), (300, 700, 0.5, 3, "tiles"),
+                                                    (200, 130, 0.1, 3, "rows"), (410, 300, 0.1, 3, "tiles")])
+def test_band_sharding_and_gather_equal_single_process(sw, sh, ov, world, balance):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, sw, sh, ov, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, sw, sh, ov, q, balance)) for r in range(world)]
     for p in procs:
         p.start()
     merged, n_tiles, stats = q.get(timeout=120)
@@ -83,14 +95,17 @@ def test_band_sharding_and_gather_equal_single_process(sw, sh, ov, world):
     # the sharded tile set is the reference's tile set (detect_glomus_test.py:264-304 restated in the oracle)
     origins, n_x, n_y, win_x, win_y, stride_x, stride_y = W.tile_grid(sw, sh, 64, 1.0, 1.0, ov, 1.0)
     assert (grid.n_x, grid.n_y, grid.win_x, grid.win_y, grid.stride_x, grid.stride_y) == (n_x, n_y, win_x, win_y, stride_x, stride_y)
-    bands = [wsi.shard_rows(grid.n_y, r, world) for r in range(world)]
-    assert np.array_equal(np.concatenate([grid.origins(r0, n) for r0, n in bands]), origins)
+    ranges = [wsi.band_tiles(grid, sh, r, world, balance)[:2] for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == grid.count and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert np.array_equal(np.concatenate([grid.origins_range(a, b) for a, b in ranges]), origins)
+    if balance == "tiles":
+        assert max(b - a for a, b in ranges) - min(b - a for a, b in ranges) <= 1          # an even split of the tiles
     assert n_tiles == grid.count
     single = _band_mask(sw, sh, grid, 0, grid.n_y, wsi.stitch_y_limit(sw, sh, 2400))
     assert np.array_equal(merged, single)
     # only the overlap rows went through the merge, and nobody shipped a whole-slide mask
-    geo = [wsi.band_rows(grid, sh, r, world) for r in range(world)]
-    assert stats["bytes_received"] == sum((y1 - y0) * sw for _, rows, y0, y1 in geo[1:] if rows)
+    geo = [wsi.band_tiles(grid, sh, r, world, balance) for r in range(world)]
+    assert stats["bytes_received"] == sum((y1 - y0) * sw for k0, k1, y0, y1 in geo[1:] if k1 > k0)
     assert stats["bytes_merged"] < stats["bytes_received"] or world == 1
 
 
