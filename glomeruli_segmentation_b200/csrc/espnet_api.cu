@@ -19,7 +19,6 @@
 #include "kernels_fp32_tma.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc_down.cuh"
-#include "kernels_tc_pair.cuh"
 #include "kernels_wsi.cuh"
 #include "kernels_frontend.cuh"
 #include "kernels_dec.cuh"
@@ -49,8 +48,7 @@ struct BlockW {
     size_t c1 = 0, d1 = 0, chain = 0, s = 0, t = 0, a = 0;
     size_t tc = 0;   // offset (bytes) into the fp16 blob for the tensor-core path: branch weights
     size_t tc_c1 = 0;   // ... and the c1 reduce weights (1x1: [CIN/8][NOUT][8]; 3x3 s2: [ks][tap][2][NOUT][8])
-    size_t tcp = 0, tc3p = 0;     // CTA-pair images of the branch weights (kernels_tc_pair.cuh): [rank][unit][tap][2][5 HB][8]
-    size_t tc3 = 0, tc3_c1 = 0;   // 3-term split copies (fp32-equivalent tensor-core path): branch [hi|lo][ks][br][tap][2][NOUT][8], 1x1 reduce [hi|lo][CIN/8][NOUT][8]
+    size_t tc3 = 0, tc3_c1 = 0;   // 3-term split copies (fp32-equivalent tensor-core path): branch weights (merged / streamed-group layouts, see the packer), 1x1 reduce [hi|lo][CIN/8][NOUT][8]
 };
 
 struct Packed {
@@ -91,7 +89,6 @@ struct espnet_handle {
     Packed pk;
     std::map<std::string, StageRef> stages;
     int fp32_impl = 1;     // fp32 mode: 1 (default) = tensor cores with 3-term fp16 operand splits (fp32-equivalent), 0 = CUDA-core FMA kernels ("fp32_impl")
-    int tc_pair = 0;       // branch stage on tensor cores: 1 = CTA pairs, cta_group::2 M = 256 MMAs (kernels_tc_pair.cuh), 0 = one CTA per tile ("tc_pair")
     int down_impl = 1;     // tensor-core 3x3-s2 reduce: 1 = TMA-staged input regions (default), 0 = per-thread global loads ("down_impl")
     int tail_impl = 0;     // 1 = run the generic run-time-class-count tail kernels even for 5 / 20 classes ("tail_impl", cross-check)
     int dec_impl = 1;      // decoder tail: 1 = 4 pixels per thread (dec_c4_kernel), 0 = 1 pixel per thread ("dec_impl")
@@ -339,66 +336,18 @@ struct Packer {
                                 dst[idx] = hi;
                                 dst[idx + (size_t)nout * 8] = lo;
                             } else {
-                                const size_t idx = (size_t)(c / 16) * unit + ((((size_t)t * 2 + (c % 16) / 8) * 5 + b) * nout + o) * 8 + (c % 8);
-                                dst[idx] = hi;
-                                dst[(size_t)ks_n * unit + idx] = lo;
+                                // streamed layout (kernels_tc_branch.cuh, BranchTcCfg): per K step [W_hi A | W_hi B | W_lo A | W_lo B], a unit =
+                                // [tap][2 chunks][branches of the group][NOUT][8]; group A = (d1, d2), group B = (d4, d8, d16)
+                                const int ga = 2, gb = 3;
+                                const size_t ua = (size_t)9 * 2 * ga * nout * 8, ub = (size_t)9 * 2 * gb * nout * 8;     // halves
+                                const bool in_a = b < ga;
+                                const int gn = in_a ? ga : gb, bl = in_a ? b : b - ga;
+                                const size_t base = (size_t)(c / 16) * 2 * unit + (in_a ? 0 : ua);
+                                const size_t idx = ((((size_t)t * 2 + (c % 16) / 8) * gn + bl) * nout + o) * 8 + (c % 8);
+                                dst[base + idx] = hi;
+                                dst[base + ua + ub + idx] = lo;
                             }
                         }
-            }
-            {   // CTA-pair images (cta_group::2 MMAs: rank r supplies accumulator columns [r N/2, (r+1) N/2) of every MMA)
-                const bool merge = ks_n == 1;
-                const HostTensor* wb[5];
-                for (int b = 0; b < 5; ++b) {
-                    wb[b] = get(key + ".d" + std::to_string(dd[b]) + ".conv.weight", {b == 0 ? n1 : n, n, 3, 3});
-                    if (!wb[b]) return false;
-                }
-                // value of accumulator column `col` of branch b, tap t, input channel c; part: 0 plain fp16, 1 hi, 2 lo
-                auto wval = [&](int part, int b, int col, int c, int t) -> uint16_t {
-                    const int co_n = b == 0 ? n1 : n;
-                    if (col >= co_n || c >= n) return 0;
-                    const float wv = wb[b]->data[((size_t)col * n + c) * 9 + t];
-                    uint16_t hi, lo;
-                    if (part == 0) { const __half hv = __float2half_rn(wv); std::memcpy(&hi, &hv, 2); return hi; }
-                    split(wv, hi, lo);
-                    return part == 1 ? hi : lo;
-                };
-                // one image set: units x ranks; colmap(unit, col in [0, nb)) -> (part, channel) or part < 0 for a zero row
-                auto build = [&](size_t& off_out, int units, int nb, auto colmap) {
-                    const int hb = nb / 2;
-                    const size_t unit_h = (size_t)9 * 2 * 5 * hb * 8;                  // halves per (rank, unit)
-                    while (blob_h.size() % 64) blob_h.push_back(0);
-                    off_out = blob_h.size() * sizeof(uint16_t);
-                    blob_h.resize(blob_h.size() + 2 * units * unit_h, 0);
-                    uint16_t* dstp = blob_h.data() + off_out / sizeof(uint16_t);
-                    for (int r = 0; r < 2; ++r)
-                        for (int u = 0; u < units; ++u)
-                            for (int t = 0; t < 9; ++t)
-                                for (int kc = 0; kc < 2; ++kc)
-                                    for (int R = 0; R < 5 * hb; ++R) {
-                                        int b, col;
-                                        if (t == 4) { const int g = r * 5 * hb + R; b = g / nb; col = g % nb; }     // centre: one N = 5 nb MMA
-                                        else { b = R / hb; col = r * hb + R % hb; }
-                                        int part, ch, ks;
-                                        colmap(u, col, part, ch, ks);
-                                        for (int j = 0; j < 8; ++j) {
-                                            const uint16_t v = part < 0 ? (uint16_t)0 : wval(part, b, ch, 16 * ks + 8 * kc + j, t);
-                                            dstp[((size_t)(r * units + u)) * unit_h + ((((size_t)t * 2 + kc) * 5 * hb + R) * 8) + j] = v;
-                                        }
-                                    }
-                };
-                build(bw.tcp, ks_n, nout, [&](int u, int col, int& part, int& ch, int& ks) { part = 0; ch = col; ks = u; });
-                if (merge) {
-                    // columns per branch: [hi 0..nout/2) | lo 0..nout/2) | hi nout/2.. | lo nout/2..); unit 1 (A_lo term): lo rows are zero
-                    build(bw.tc3p, 2, 2 * nout, [&](int u, int col, int& part, int& ch, int& ks) {
-                        const int half = col / nout, w = col % nout;            // half = rank that supplies the row
-                        const bool lo = w >= nout / 2;
-                        ch = half * (nout / 2) + w % (nout / 2);
-                        part = lo ? (u == 0 ? 2 : -1) : 1;
-                        ks = 0;
-                    });
-                } else {
-                    build(bw.tc3p, 2 * ks_n, nout, [&](int u, int col, int& part, int& ch, int& ks) { part = u < ks_n ? 1 : 2; ch = col; ks = u % ks_n; });
-                }
             }
             if (down) {    // 3x3 stride-2 reduce: [hi|lo][ks][tap][2][NOUT][8]
                 const int nout1 = 8 * nkc, ks1 = (cin + 15) / 16;
@@ -720,30 +669,6 @@ int run_branch_tc(espnet_t* h, const BlockW& bw, const __half* o1h, const float*
     int rc = make_o1h_map(h, &map, o1h, SPLIT ? 2 * B : B, NKC, H, W, kTcBoxW, kTcBoxH, 2);
     if (rc) return rc;
     const long long tiles = (long long)B * ((H + kTcTileH - 1) / kTcTileH) * ((W + kTcTileW - 1) / kTcTileW);
-    if (h->tc_pair) {
-        // clusters of two CTAs, one cta_group::2 MMA covers both tiles of a pair
-        using PCfg = BranchPairCfg<NKC, NOUT, SPLIT>;
-        p.w = reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3p : bw.tcp));
-        auto q0 = esp_branch_tc_pair_kernel<NKC, NOUT, CO1, CO, 0, SPLIT>;
-        auto q1 = esp_branch_tc_pair_kernel<NKC, NOUT, CO1, CO, 1, SPLIT>;
-        auto q2 = esp_branch_tc_pair_kernel<NKC, NOUT, CO1, CO, 2, SPLIT>;
-        auto pk = var == 0 ? q0 : (var == 1 ? q1 : q2);
-        rc = set_smem(h, pk, PCfg::SMEM);
-        if (rc) return rc;
-        const long long pairs = (tiles + 1) / 2;
-        const int npairs = (int)std::min<long long>(pairs, std::max(1, h->num_sms / 2));
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * npairs); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = PCfg::SMEM; cfg.stream = st;
-        cudaLaunchAttribute attr{};
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        { ProfScope _ps(h, SPLIT ? (NKC == 2 ? "esp_branch_tc3_l2" : "esp_branch_tc3_l3") : (NKC == 2 ? "esp_branch_tc_l2" : "esp_branch_tc_l3"), st);
-          CUDA_TRY(h, cudaLaunchKernelEx(&cfg, pk, map, p)); }
-        LAUNCH_COUNT();
-        CUDA_TRY(h, cudaPeekAtLastError());
-        return ESPNET_OK;
-    }
     auto k0 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 0, SPLIT>;
     auto k1 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 1, SPLIT>;
     auto k2 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 2, SPLIT>;
@@ -1017,7 +942,6 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (std::strcmp(key, "dec_impl") == 0 && value >= 0 && value <= 1) { h->dec_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "down_impl") == 0 && value >= 0 && value <= 1) { h->down_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "tail_impl") == 0 && value >= 0 && value <= 1) { h->tail_impl = value; return ESPNET_OK; }
-    if (std::strcmp(key, "tc_pair") == 0 && value >= 0 && value <= 1) { h->tc_pair = value; return ESPNET_OK; }
     if (std::strcmp(key, "l2_reverse") == 0 && value >= 0 && value <= 1) { h->l2_reverse = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 2) { h->tc_reduce = value; return ESPNET_OK; }
     return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);

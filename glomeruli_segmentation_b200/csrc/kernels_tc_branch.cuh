@@ -50,9 +50,6 @@ constexpr int kTcPrefetchLead = ESPNET_TC_PREFETCH_LEAD;
 // arithmetic and the predicate tests lengthen the single-thread issue loop, so the default issues every tap.
 #define ESPNET_TC_NOSKIP 1
 #endif
-#ifndef ESPNET_TC_NOWSTREAM
-#define ESPNET_TC_NOWSTREAM 0   // 1: TIMING EXPERIMENT ONLY (wrong results): load the streamed split weights once
-#endif   // tiles the L2 prefetcher runs ahead of the epilogue
 
 struct BranchTcParams {
     const __half* w;        // [9][NKC][5][NOUT][8] fp16 (d1, d2, d4, d8, d16); split variants: see BranchTcCfg
@@ -69,16 +66,22 @@ template <int NKC, int NOUT, bool SPLIT = false>
 struct BranchTcCfg {
     static constexpr int KS = NKC / 2;                            // K = 16 steps per tile
     static constexpr int W_BRANCH = 9 * NKC * NOUT * 16;          // bytes of one branch's weights (plain layout)
-    static constexpr int W_UNIT = 5 * 9 * 2 * NOUT * 16;          // split layout [tap][2][br][NOUT][8]: one K step, hi OR lo
-    static constexpr bool W_STREAM = SPLIT && KS > 1;             // split weights do not fit: 2-unit ring, else resident
+    static constexpr bool W_STREAM = SPLIT && KS > 1;             // split weights do not fit: streamed in four units per K step
     static constexpr bool MERGE = SPLIT && KS == 1;               // one K step: [tap][2][br][hi NOUT | lo NOUT][8], resident
     static constexpr int NB = MERGE ? 2 * NOUT : NOUT;            // weight rows = accumulator columns per branch
-    static constexpr int W_BYTES = SPLIT ? 2 * W_UNIT : 5 * W_BRANCH;
+    // streamed split layout: per K step four units [tap][2 chunks][branches of the group][NOUT][8]: W_hi group A (d1, d2),
+    // W_hi group B (d4, d8, d16), W_lo group A, W_lo group B (see the kernel comment for why two branch groups)
+    static constexpr int GA = 2, GB = 3;
+    static constexpr int UA = 9 * 2 * GA * NOUT * 16, UB = 9 * 2 * GB * NOUT * 16;
+    static constexpr int OFF_HIA = 0, OFF_HIB = UA, OFF_LOA = UA + UB, OFF_LOB = 2 * UA + UB;
+    static constexpr int W_KSTEP = 2 * (UA + UB);                 // bytes of one K step's hi + lo weights
+    static constexpr int W_BYTES = SPLIT ? W_KSTEP : 5 * W_BRANCH;
     static constexpr int ACC_COLS = 5 * NB;                       // TMEM columns per tile
     static constexpr int TMEM_COLS = (kTcAccStages * ACC_COLS <= 256) ? 256 : 512;
     static constexpr int EP_BYTES = 2 * 128 * 16;                 // two float4 tables of 128 channels
     static constexpr size_t SMEM = 1024 + 2 * (size_t)kTcStage + (size_t)W_BYTES + EP_BYTES + 256;
     static_assert(kTcAccStages * ACC_COLS <= 512, "TMEM columns");
+    static_assert(!MERGE || W_BYTES == 5 * 9 * 2 * 2 * NOUT * 16, "merged layout size");
 };
 
 // VAR: 0 = DownSamplerB (no residual, writes out and out2), 1 = ESP block (residual, out), 2 = last ESP block of a level
@@ -88,9 +91,16 @@ struct BranchTcCfg {
 // 3-term fp16 splits, a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with a_hi = fp16(a/4), a_lo = fp16(a/4 - a_hi),
 // w_hi = fp16(4w), w_lo = fp16(4w - w_hi): 22-bit mantissa products, fp32 accumulation in TMEM.  o1 arrives as two
 // chunk-plane tensors (hi crops [0,B), lo crops [B,2B) of one tensor map); per K step the hi half-box goes to stage
-// 0 and the lo half-box to stage 1, and the weights [hi|lo][K step][branch][tap][2][NOUT][8] stream through a 2-unit
-// ring (unit 0 = W_hi(k), unit 1 = W_lo(k)) because hi + lo of all branches (180 KB) do not fit next to the boxes.
-// MMA order per K step: A_lo x W_hi, A_hi x W_hi, A_hi x W_lo -- 3x the MMAs of the plain variant.
+// 0 and the lo half-box to stage 1.  Two K steps (level 3): hi + lo weights of all branches (180 KB) do not fit next to the
+// boxes, they stream per K step.  The two MMAs that share A_hi -- A_hi x W_hi and A_hi x W_lo -- are issued back to back
+// with the A COLLECTOR (tc::umma_f16_keep_a / umma_f16_reuse_a): the second one does not re-read its 4 KB window from shared
+// memory, 76 instead of 114 cycles per pair.  That needs W_hi(k) and W_lo(k) at the same time and W_hi(k) again for
+// A_lo x W_hi, so a plain two-unit ring would leave no time to fetch W_hi(k+1).  The branches are therefore split in two
+// groups, A = (d1, d2) and B = (d4, d8, d16), each with its own W_hi / W_lo unit, and a K step runs four phases
+//     P0: A_hi x {W_hi, W_lo}(A)   P1: A_hi x {W_hi, W_lo}(B)   P2: A_lo x W_hi(A)   P3: A_lo x W_hi(B)
+// so that every unit is idle for at least one phase before it is needed again: W_lo(A) after P0, W_lo(B) and the A_hi box
+// after P1, W_hi(A) after P2 (refilled during P3), W_hi(B) and the A_lo box after P3 (refilled during the next P0).  The
+// producer refills in exactly that order.  (41 + 82) MMAs per K step as before, 2 x 41 of them at the pair rate.
 // With a single K step (level 2, Cfg::MERGE) TMEM has room for separate hi / lo accumulators: the weights are resident
 // as [W_hi | W_lo] rows, A_hi x [W_hi | W_lo] is ONE N = 2 NOUT MMA, A_lo x W_hi a second one, and the epilogue adds the
 // two accumulator halves -- 2x the MMAs of the plain variant.
@@ -108,11 +118,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sep4) + Cfg::EP_BYTES);
     uint64_t* a_full = bars + 0;      // [2]
     uint64_t* a_empty = bars + 2;     // [2]
-    uint64_t* w_full = bars + 4;      // [2] (plain variant: only [0])
-    uint64_t* w_empty = bars + 6;     // [2] (streamed split weights only)
-    uint64_t* acc_full = bars + 8;    // [3]
-    uint64_t* acc_empty = bars + 11;  // [3]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* w_full = bars + 4;      // [4] streamed split weights: hi A, hi B, lo A, lo B (other variants: only [0])
+    uint64_t* w_empty = bars + 8;     // [4] (streamed split weights only)
+    uint64_t* acc_full = bars + 12;   // [3]
+    uint64_t* acc_empty = bars + 15;  // [3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
     uint32_t* epi_done = tmem_slot + 1;   // tiles finished by epilogue warp 0 (throttle of the L2 prefetcher)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -125,8 +135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
         if ((tc::smem_addr(abuf) & 127u) != 0) __trap();   // TMA destination alignment
         tc::mbar_init(a_full + 0, 1); tc::mbar_init(a_full + 1, 1);
         tc::mbar_init(a_empty + 0, 1); tc::mbar_init(a_empty + 1, 1);
-        tc::mbar_init(w_full + 0, 1); tc::mbar_init(w_full + 1, 1);
-        tc::mbar_init(w_empty + 0, 1); tc::mbar_init(w_empty + 1, 1);
+        for (int u = 0; u < 4; ++u) { tc::mbar_init(w_full + u, 1); tc::mbar_init(w_empty + u, 1); }
         for (int s = 0; s < kTcAccStages; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 16); }
         *epi_done = 0;
         tc::mbar_fence_init();
@@ -179,9 +188,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                     tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 0, b + p.B);
                 }
             } else {
-                // per K step n: W_hi(k) -> unit 0, A_lo(k) -> stage 1, A_hi(k) -> stage 0, W_lo(k) -> unit 1 (the order in
-                // which the MMA issuer frees / needs them)
+                // per K step n, in the order in which the MMA issuer frees the buffers during the previous K step:
+                // W_lo(A), W_lo(B), A_hi -> stage 0, W_hi(A), W_hi(B), A_lo -> stage 1
                 const uint8_t* wg = reinterpret_cast<const uint8_t*>(p.w);
+                auto load_w = [&](int u, int off, int bytes, int ks, uint32_t par) {
+                    tc::mbar_wait(w_empty + u, par ^ 1);
+                    tc::mbar_expect_tx(w_full + u, bytes);
+                    tc::bulk_g2s(wbuf + off, wg + (size_t)ks * Cfg::W_KSTEP + off, bytes, w_full + u);
+                };
                 int n = 0;
                 for (int it = 0; it < my_tiles; ++it) {
                     const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -190,22 +204,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks, ++n) {
                         const uint32_t par = (uint32_t)(n & 1);
-                        tc::mbar_wait(a_empty + 1, par ^ 1);
-                        tc::mbar_expect_tx(a_full + 1, kTcStage);
-                        tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 2 * ks, b + p.B);
-                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) {
-                            if (!ESPNET_TC_NOWSTREAM) tc::mbar_wait(w_empty + 0, par ^ 1);
-                            tc::mbar_expect_tx(w_full + 0, Cfg::W_UNIT);
-                            tc::bulk_g2s(wbuf, wg + (size_t)ks * Cfg::W_UNIT, Cfg::W_UNIT, w_full + 0);
-                        }
+                        load_w(2, Cfg::OFF_LOA, Cfg::UA, ks, par);
+                        load_w(3, Cfg::OFF_LOB, Cfg::UB, ks, par);
                         tc::mbar_wait(a_empty + 0, par ^ 1);
                         tc::mbar_expect_tx(a_full + 0, kTcStage);
                         tc::tma_load_4d(abuf, &tmap, a_full + 0, cx, cy, 2 * ks, b);
-                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) {
-                            if (!ESPNET_TC_NOWSTREAM) tc::mbar_wait(w_empty + 1, par ^ 1);
-                            tc::mbar_expect_tx(w_full + 1, Cfg::W_UNIT);
-                            tc::bulk_g2s(wbuf + Cfg::W_UNIT, wg + (size_t)(KS + ks) * Cfg::W_UNIT, Cfg::W_UNIT, w_full + 1);
-                        }
+                        load_w(0, Cfg::OFF_HIA, Cfg::UA, ks, par);
+                        load_w(1, Cfg::OFF_HIB, Cfg::UB, ks, par);
+                        tc::mbar_wait(a_empty + 1, par ^ 1);
+                        tc::mbar_expect_tx(a_full + 1, kTcStage);
+                        tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 2 * ks, b + p.B);
                     }
                 }
             }
@@ -320,32 +328,84 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                                acc_full + as, nullptr);
                 }
             } else {
-                constexpr uint32_t TAP = 2 * 5 * NOUT;                       // split weight layout: tap stride (16 B units)
+                // One phase = one branch group against one A half-box.  PAIR: A_hi x W_hi keeps A in the collector, A_hi x W_lo
+                // reuses it; otherwise single MMAs (A_lo x W_hi).  The centre tap of the group's branches is one N = GN * NOUT
+                // MMA (the group's branches are adjacent rows in the unit and adjacent accumulator columns).
+                auto issue_group = [&](auto gn_tag, auto pair_tag, uint32_t a_lo_s, uint32_t bh, uint32_t bl, int br0, uint32_t d_tile, bool fresh,
+                                       uint64_t* c0, uint64_t* c1, uint64_t* c2) {
+                    constexpr int GN = decltype(gn_tag)::value;
+                    constexpr bool PAIR = decltype(pair_tag)::value != 0;
+                    constexpr uint32_t idesc = tc::umma_idesc_f16(NOUT), idesc_c = tc::umma_idesc_f16(GN * NOUT);
+                    constexpr uint32_t TAP = 2 * GN * NOUT;                      // tap stride inside a unit (16 B units)
+                    constexpr uint32_t lbo = ((uint32_t)((GN * NOUT * 16) >> 4) << 16);   // K chunk stride = GN * NOUT rows
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        const uint64_t adesc_c = ((uint64_t)a_hi << 32) | (uint64_t)a_lo_s;
+                        const uint32_t d_g = d_tile + (uint32_t)(br0 * NOUT);
+                        {
+                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(bh + lbo + 4u * TAP);
+                            if constexpr (PAIR) {
+                                tc::umma_f16_keep_a(d_g, adesc_c, bdesc, idesc_c, fresh ? 0u : 1u);
+                                tc::umma_f16_reuse_a(d_g, adesc_c, ((uint64_t)b_hi << 32) | (uint64_t)(bl + lbo + 4u * TAP), idesc_c);
+                            } else {
+                                tc::umma_f16(d_g, adesc_c, bdesc, idesc_c, fresh ? 0u : 1u);
+                            }
+                        }
+#pragma unroll 1
+                        for (int g = 0; g < GN; ++g) {
+                            const int d = 1 << (br0 + g), dp = d * kTcBoxW;
+                            const uint32_t d_tmem = d_g + (uint32_t)(g * NOUT);
+                            const uint32_t bh_g = bh + lbo + (uint32_t)(g * NOUT), bl_g = bl + lbo + (uint32_t)(g * NOUT);
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                if (tap == 4) continue;
+                                const int ky = tap / 3 - 1, kx = tap % 3 - 1;       // compile-time after unrolling
+                                const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_s + (uint32_t)(ky * dp + kx * d));
+                                const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(bh_g + (uint32_t)tap * TAP);
+                                if constexpr (PAIR) {
+                                    tc::umma_f16_keep_a(d_tmem, adesc, bdesc, idesc, 1u);
+                                    tc::umma_f16_reuse_a(d_tmem, adesc, ((uint64_t)b_hi << 32) | (uint64_t)(bl_g + (uint32_t)tap * TAP), idesc);
+                                } else {
+                                    tc::umma_f16(d_tmem, adesc, bdesc, idesc, 1u);
+                                }
+                            }
+                        }
+                        if (c0) tc::umma_commit(c0);
+                        if (c1) tc::umma_commit(c1);
+                        if (c2) tc::umma_commit(c2);
+                    }
+                    __syncwarp();
+                };
                 const uint32_t a_st0 = a_lo0, a_st1 = a_lo0 + (uint32_t)(kTcStage >> 4);
-                const uint32_t w_u0 = b_lo0, w_u1 = b_lo0 + (uint32_t)(Cfg::W_UNIT >> 4);
+                const uint32_t w0 = tc::smem_addr(wbuf) >> 4;
+                const uint32_t w_hia = w0 + (uint32_t)(Cfg::OFF_HIA >> 4), w_hib = w0 + (uint32_t)(Cfg::OFF_HIB >> 4);
+                const uint32_t w_loa = w0 + (uint32_t)(Cfg::OFF_LOA >> 4), w_lob = w0 + (uint32_t)(Cfg::OFF_LOB >> 4);
                 int n = 0;
                 for (int it = 0; it < my_tiles; ++it) {
                     const int as = it % kTcAccStages;
-                    const uint32_t vm = tap_mask(it);
                     tc::mbar_wait(acc_empty + as, (uint32_t)(((it / kTcAccStages) & 1) ^ 1));
                     const uint32_t d_tile = tmem_base + (uint32_t)(as * Cfg::ACC_COLS);
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks, ++n) {
                         const uint32_t par = (uint32_t)(n & 1);
-                        // (1) A_lo x W_hi
-                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) tc::mbar_wait(w_full + 0, par);
+                        // P0: A_hi x {W_hi, W_lo}, group A
+                        tc::mbar_wait(w_full + 2, par);
+                        tc::mbar_wait(a_full + 0, par);
+                        tc::mbar_wait(w_full + 0, par);
+                        __syncwarp();
+                        issue_group(IntTag<Cfg::GA>(), IntTag<1>(), a_st0, w_hia, w_loa, 0, d_tile, ks == 0, w_empty + 2, nullptr, nullptr);
+                        // P1: A_hi x {W_hi, W_lo}, group B
+                        tc::mbar_wait(w_full + 3, par);
+                        tc::mbar_wait(w_full + 1, par);
+                        __syncwarp();
+                        issue_group(IntTag<Cfg::GB>(), IntTag<1>(), a_st0, w_hib, w_lob, Cfg::GA, d_tile, ks == 0, w_empty + 3, a_empty + 0, nullptr);
+                        // P2: A_lo x W_hi, group A
                         tc::mbar_wait(a_full + 1, par);
                         __syncwarp();
-                        issue_step(IntTag<NOUT>(), IntTag<1>(), a_st1, w_u0, TAP, d_tile, ks == 0, vm, a_empty + 1, nullptr, nullptr);
-                        // (2) A_hi x W_hi
-                        tc::mbar_wait(a_full + 0, par);
-                        __syncwarp();
-                        issue_step(IntTag<NOUT>(), IntTag<1>(), a_st0, w_u0, TAP, d_tile, false, vm, w_empty + 0, nullptr, nullptr);
-                        // (3) A_hi x W_lo
-                        if (ESPNET_TC_NOWSTREAM ? n == 0 : true) tc::mbar_wait(w_full + 1, par);
-                        __syncwarp();
-                        issue_step(IntTag<NOUT>(), IntTag<1>(), a_st0, w_u1, TAP, d_tile, false, vm, a_empty + 0, w_empty + 1,
-                                   ks == KS - 1 ? acc_full + as : nullptr);
+                        issue_group(IntTag<Cfg::GA>(), IntTag<0>(), a_st1, w_hia, 0u, 0, d_tile, false, w_empty + 0, nullptr, nullptr);
+                        // P3: A_lo x W_hi, group B
+                        issue_group(IntTag<Cfg::GB>(), IntTag<0>(), a_st1, w_hib, 0u, Cfg::GA, d_tile, false, w_empty + 1, a_empty + 1,
+                                    ks == KS - 1 ? acc_full + as : nullptr);
                     }
                 }
             }

@@ -97,8 +97,7 @@ ESPNET_API int espnet_pack_weights(espnet_t* h, const espnet_tensor_desc* tensor
 ESPNET_API int espnet_set_mode(espnet_t* h, int mode);            /* ESPNET_MODE_* ; default FP32 */
 /* Options: "fp32_impl" (see ESPNET_MODE_FP32); "branch_impl" (CUDA-core fp32 branch kernel: 0 auto, 1 per-thread global
  * loads, 2 TMA-staged shared-memory halo tiles); "tc_reduce" (tensor-core modes: 1 = reduce convs on tensor cores, 0 = CUDA
- * cores); "tc_pair" (tensor-core branch stage: 0 = one CTA per MMA tile (default), 1 = clusters of two CTAs with
- * tcgen05 cta_group::2 M = 256 MMAs -- bit-identical results); "l2_reverse" (1x1 reduce walks its tiles against the
+ * cores); "l2_reverse" (1x1 reduce walks its tiles against the
  * producer's order to start on the L2-resident part, default 1); "dec_impl" (decoder tail: 1 = 4 pixels per thread); "down_impl" (tensor-core 3x3-s2 reduce: 1 = TMA-staged input regions (default), 0 = per-thread global loads; bit-identical);
  * "tail_impl" (1 = generic run-time-class-count tail kernels even for 5 / 20
  * classes; bit-identical to the scalar specialised ones). */

@@ -145,42 +145,9 @@ def test_split_path_multi_tile_per_cta_and_determinism(fold_sd):
     assert torch.equal(m.segment(big, mean, std), mb)
 
 
-# ---- CTA pairs (cta_group::2 MMAs, kernels_tc_pair.cuh): option "tc_pair" ------------------------------------------------
-@pytest.mark.parametrize("mode", ["fp32", "f16tc"])
-@pytest.mark.parametrize("B,H,W", [(1, 8, 8), (1, 24, 40), (3, 72, 40), (1, 264, 328), (2, 512, 512)])
-def test_pair_kernels_bit_equal_single_cta(fold_sd, mode, B, H, W):
-    """Same fp16 products, same accumulation order: the M = 256 pair MMAs must reproduce the single-CTA kernels bit for
-    bit, including odd tile counts (one CTA of the last pair idles on a dummy tile) and partial tiles."""
-    sd = fold_sd(1)
-    mean, std = FOLD_MEAN_STD[1]
-    u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=11 * H + W, sigma=3.0)).to(DEV)
-    m = _model(sd, mode)
-    la, lb = torch.empty((B, 5, H, W), device=DEV), torch.empty((B, 5, H, W), device=DEV)
-    ma = m.set_option("tc_pair", 0).segment(u8, mean, std, logits=la).clone()
-    mb = m.set_option("tc_pair", 1).segment(u8, mean, std, logits=lb)
-    assert torch.equal(la, lb)
-    assert torch.equal(ma, mb)
-
-
-def test_pair_kernels_against_oracle_and_ring_wraparound(fold_sd):
-    """fp32 bar against the CPU oracle through the pair kernels, then many pair iterations per cluster."""
-    sd = fold_sd(3)
-    mean, std = FOLD_MEAN_STD[3]
-    u8 = O.synth_crops("D1", 2, 256, 256, seed=5)
-    ref = O.espnet_forward(sd, torch.from_numpy(O.normalise_bgr_u8(u8, mean, std)))
-    m = _model_split(sd).set_option("tc_pair", 1)
-    lg = torch.empty((2, 5, 256, 256), device=DEV)
-    m.segment(torch.from_numpy(u8).to(DEV), mean, std, logits=lg)
-    assert (lg.cpu() - ref).abs().max().item() <= LOGIT_TOL
-    big = torch.from_numpy(u8).to(DEV).repeat(75, 1, 1, 1)
-    lb = torch.empty((150, 5, 256, 256), device=DEV)
-    m.segment(big, mean, std, logits=lb)
-    assert torch.equal(lb[148:150], lg) and torch.equal(lb[:2], lg)
-
-
 def test_random_shapes_all_paths_agree(fold_sd):
     """Seeded sweep over odd crop geometries (partial MMA tiles in both directions, one-tile maps, odd tile counts):
-    tensor-core split path vs the CUDA-core fp32 path within the fp32 bar, CTA-pair kernels bit-equal to single-CTA."""
+    tensor-core split path vs the CUDA-core fp32 path within the fp32 bar, and run-to-run bit-equal."""
     sd = fold_sd(5)
     mean, std = FOLD_MEAN_STD[5]
     rng = np.random.default_rng(2024)
@@ -192,26 +159,24 @@ def test_random_shapes_all_paths_agree(fold_sd):
         u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=int(rng.integers(1 << 30)), sigma=3.0)).to(DEV)
         l0, l1, l2 = (torch.empty((B, 5, H, W), device=DEV) for _ in range(3))
         m_cc.segment(u8, mean, std, logits=l0)
-        m_tc.set_option("tc_pair", 0).segment(u8, mean, std, logits=l1)
-        m_tc.set_option("tc_pair", 1).segment(u8, mean, std, logits=l2)
+        m_tc.segment(u8, mean, std, logits=l1)
+        m_tc.segment(u8, mean, std, logits=l2)
         assert (l1 - l0).abs().max().item() <= LOGIT_TOL, (B, H, W)
         assert torch.equal(l1, l2), (B, H, W)
 
 
 def test_large_crop_paths_agree(fold_sd):
     """One 2048 x 2048 crop (256 x 256 level-3 map, 32 768 MMA tiles at level 2): split tensor-core path vs the CUDA-core
-    fp32 path within the fp32 bar, pair kernels bit-equal, f16tc masks within the agreement bar of the fp32 masks."""
+    fp32 path within the fp32 bar, f16tc masks within the agreement bar of the fp32 masks."""
     sd = fold_sd(1)
     mean, std = FOLD_MEAN_STD[1]
     B, H, W = 1, 2048, 2048
     u8 = torch.from_numpy(O.synth_crops("D2", B, H, W, seed=99, sigma=3.0)).to(DEV)
-    l0, l1, l2 = (torch.empty((B, 5, H, W), device=DEV) for _ in range(3))
+    l0, l1 = (torch.empty((B, 5, H, W), device=DEV) for _ in range(2))
     m0 = _model(sd, "fp32").set_option("fp32_impl", 0).segment(u8, mean, std, logits=l0)
     m_tc = _model_split(sd)
-    m1 = m_tc.set_option("tc_pair", 0).segment(u8, mean, std, logits=l1).clone()
-    m_tc.set_option("tc_pair", 1).segment(u8, mean, std, logits=l2)
+    m1 = m_tc.segment(u8, mean, std, logits=l1).clone()
     assert (l1 - l0).abs().max().item() <= LOGIT_TOL
-    assert torch.equal(l1, l2)
     assert (m1 == m0).float().mean().item() >= 0.9999
     mh = _model(sd, "f16tc").segment(u8, mean, std)
     assert (mh == m0).float().mean().item() >= AGREE
