@@ -89,6 +89,7 @@ struct espnet_handle {
     Packed pk;
     std::map<std::string, StageRef> stages;
     int fp32_impl = 1;     // fp32 mode: 1 (default) = tensor cores with 3-term fp16 operand splits (fp32-equivalent), 0 = CUDA-core FMA kernels ("fp32_impl")
+    int dbg = 0;           // timing experiments inside the level-3 split branch kernel (wrong results), see BranchTcParams::dbg
     int down_impl = 1;     // tensor-core 3x3-s2 reduce: 1 = TMA-staged input regions (default), 0 = per-thread global loads ("down_impl")
     int tail_impl = 0;     // 1 = run the generic run-time-class-count tail kernels even for 5 / 20 classes ("tail_impl", cross-check)
     int dec_impl = 1;      // decoder tail: 1 = 4 pixels per thread (dec_c4_kernel), 0 = 1 pixel per thread ("dec_impl")
@@ -663,6 +664,7 @@ int run_branch_tc(espnet_t* h, const BlockW& bw, const __half* o1h, const float*
     p.s2 = h->dparams + s2; p.t2 = h->dparams + t2; p.a2 = h->dparams + a2;
     p.out2 = out2; p.C2 = C2; p.c2_off = c2_off;
     p.B = B; p.H = H; p.W = W;
+    p.dbg = h->dbg;
     const int var = res == nullptr ? 0 : (out != nullptr ? 1 : 2);
     if ((var == 0 && (!out || !out2)) || (var == 2 && !out2)) return fail(h, ESPNET_EINVAL, "run_branch_tc: unsupported output combination");
     CUtensorMap map;
@@ -940,6 +942,12 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     if (std::strcmp(key, "branch_impl") == 0 && value >= 0 && value <= 2) { h->branch_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "fp32_impl") == 0 && value >= 0 && value <= 1) { h->fp32_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "dec_impl") == 0 && value >= 0 && value <= 1) { h->dec_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "dbg") == 0 && value >= 0 && value <= 7) {
+        if (value != 0 && !ESPNET_TC_TIMING_EXPERIMENTS)
+            return fail(h, ESPNET_EINVAL, "espnet_set_option: \"dbg\" (timing experiments with wrong results) needs a library built with -DESPNET_TC_TIMING_EXPERIMENTS=1");
+        h->dbg = value;
+        return ESPNET_OK;
+    }
     if (std::strcmp(key, "down_impl") == 0 && value >= 0 && value <= 1) { h->down_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "tail_impl") == 0 && value >= 0 && value <= 1) { h->tail_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "l2_reverse") == 0 && value >= 0 && value <= 1) { h->l2_reverse = value; return ESPNET_OK; }

@@ -60,7 +60,14 @@ struct BranchTcParams {
     float* out2;            // [B,C2,H,W] or nullptr (second BR straight into the following concat buffer)
     int C2, c2_off;
     int B, H, W;
+    int dbg;                // TIMING EXPERIMENTS ONLY (wrong results; honoured only when the library is built with
+                            // -DESPNET_TC_TIMING_EXPERIMENTS=1): bit 0 = stream the split weights only for the first tile, bit 1 = load
+                            // the A boxes only for the first tile, bit 2 = epilogue without global loads / stores (option "dbg")
 };
+#ifndef ESPNET_TC_TIMING_EXPERIMENTS
+#define ESPNET_TC_TIMING_EXPERIMENTS 0
+#endif
+__device__ __forceinline__ int tc_dbg(const BranchTcParams& p) { return ESPNET_TC_TIMING_EXPERIMENTS ? p.dbg : 0; }
 
 template <int NKC, int NOUT, bool SPLIT = false>
 struct BranchTcCfg {
@@ -191,12 +198,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                 // per K step n, in the order in which the MMA issuer frees the buffers during the previous K step:
                 // W_lo(A), W_lo(B), A_hi -> stage 0, W_hi(A), W_hi(B), A_lo -> stage 1
                 const uint8_t* wg = reinterpret_cast<const uint8_t*>(p.w);
+                const bool dw = tc_dbg(p) & 1, da = tc_dbg(p) & 2;
+                int n = 0;
                 auto load_w = [&](int u, int off, int bytes, int ks, uint32_t par) {
+                    if (dw && n >= KS) return;
                     tc::mbar_wait(w_empty + u, par ^ 1);
                     tc::mbar_expect_tx(w_full + u, bytes);
                     tc::bulk_g2s(wbuf + off, wg + (size_t)ks * Cfg::W_KSTEP + off, bytes, w_full + u);
                 };
-                int n = 0;
                 for (int it = 0; it < my_tiles; ++it) {
                     const int tile = (int)blockIdx.x + it * (int)gridDim.x;
                     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
@@ -206,14 +215,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
                         const uint32_t par = (uint32_t)(n & 1);
                         load_w(2, Cfg::OFF_LOA, Cfg::UA, ks, par);
                         load_w(3, Cfg::OFF_LOB, Cfg::UB, ks, par);
-                        tc::mbar_wait(a_empty + 0, par ^ 1);
-                        tc::mbar_expect_tx(a_full + 0, kTcStage);
-                        tc::tma_load_4d(abuf, &tmap, a_full + 0, cx, cy, 2 * ks, b);
+                        if (!(da && n >= KS)) {
+                            tc::mbar_wait(a_empty + 0, par ^ 1);
+                            tc::mbar_expect_tx(a_full + 0, kTcStage);
+                            tc::tma_load_4d(abuf, &tmap, a_full + 0, cx, cy, 2 * ks, b);
+                        }
                         load_w(0, Cfg::OFF_HIA, Cfg::UA, ks, par);
                         load_w(1, Cfg::OFF_HIB, Cfg::UB, ks, par);
-                        tc::mbar_wait(a_empty + 1, par ^ 1);
-                        tc::mbar_expect_tx(a_full + 1, kTcStage);
-                        tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 2 * ks, b + p.B);
+                        if (!(da && n >= KS)) {
+                            tc::mbar_wait(a_empty + 1, par ^ 1);
+                            tc::mbar_expect_tx(a_full + 1, kTcStage);
+                            tc::tma_load_4d(abuf + kTcStage, &tmap, a_full + 1, cx, cy, 2 * ks, b + p.B);
+                        }
                     }
                 }
             }
@@ -388,19 +401,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks, ++n) {
                         const uint32_t par = (uint32_t)(n & 1);
+                        const bool ww = !((tc_dbg(p) & 1) && n >= KS), wa = !((tc_dbg(p) & 2) && n >= KS);
                         // P0: A_hi x {W_hi, W_lo}, group A
-                        tc::mbar_wait(w_full + 2, par);
-                        tc::mbar_wait(a_full + 0, par);
-                        tc::mbar_wait(w_full + 0, par);
+                        if (ww) tc::mbar_wait(w_full + 2, par);
+                        if (wa) tc::mbar_wait(a_full + 0, par);
+                        if (ww) tc::mbar_wait(w_full + 0, par);
                         __syncwarp();
                         issue_group(IntTag<Cfg::GA>(), IntTag<1>(), a_st0, w_hia, w_loa, 0, d_tile, ks == 0, w_empty + 2, nullptr, nullptr);
                         // P1: A_hi x {W_hi, W_lo}, group B
-                        tc::mbar_wait(w_full + 3, par);
-                        tc::mbar_wait(w_full + 1, par);
+                        if (ww) tc::mbar_wait(w_full + 3, par);
+                        if (ww) tc::mbar_wait(w_full + 1, par);
                         __syncwarp();
                         issue_group(IntTag<Cfg::GB>(), IntTag<1>(), a_st0, w_hib, w_lob, Cfg::GA, d_tile, ks == 0, w_empty + 3, a_empty + 0, nullptr);
                         // P2: A_lo x W_hi, group A
-                        tc::mbar_wait(a_full + 1, par);
+                        if (wa) tc::mbar_wait(a_full + 1, par);
                         __syncwarp();
                         issue_group(IntTag<Cfg::GA>(), IntTag<0>(), a_st1, w_hia, 0u, 0, d_tile, false, w_empty + 0, nullptr, nullptr);
                         // P3: A_lo x W_hi, group B
@@ -451,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
             const int y = ty * kTcTileH + row, x = tx * kTcTileW + col;
-            const bool valid = (y < H) && (x < W);
+            const bool valid = (y < H) && (x < W) && !(tc_dbg(p) & 4);
             const size_t pix = valid ? (size_t)y * W + x : 0;
             // byte pointers to channel 0 of this pixel; a channel is "+ ch * plane_b" = one IMAD.WIDE.U32
             const char* res_b = HAS_RES ? reinterpret_cast<const char*>(p.res + (size_t)b * C * plane + pix) : nullptr;
