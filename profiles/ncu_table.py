@@ -22,6 +22,7 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1.0, "ms":
 
 def short(name):
     name = re.sub(r"^void ", "", name)
+    name = re.sub(r"\((int|bool)\)", "", name)
     name = re.sub(r"\(.*$", "", name)
     return name.replace("espnet::", "")
 
@@ -40,7 +41,7 @@ def main():
         for key, m in M.items():
             if key in ("grid", "block") or m not in col or r[col[m]] == "":
                 continue
-            v = float(r[col[m]].replace(",", "")) * SCALE.get(units[col[m]], 1.0)
+            v = float(r[col[m]].replace(",", "")) * SCALE.get(units[col[m]].split("/")[0], 1.0)
             a[key] = a.get(key, 0.0) + v
     print("# %s   (cold-cache, serialised launches: compare shares and per-launch DRAM bytes, not absolute times)" % rep)
     print("%-58s %3s %9s %9s %9s %6s %6s %6s %6s %6s %6s %6s %5s %7s" % ("kernel", "n", "us/launch", "rd MB", "wr MB", "dram%", "tens%", "tc%", "tcsm%", "fma%", "issue%", "L2hit%", "regs", "smemKB"))
