@@ -1396,8 +1396,9 @@ static int stitch_grid_launch(uint8_t* out, int out_y0, int out_rows, int slide_
     if (ylo < out_y0) ylo = out_y0;
     if (yhi > (long long)out_y0 + out_rows) yhi = (long long)out_y0 + out_rows;
     if (yhi <= ylo) return ESPNET_OK;
-    int gx = (slide_w + 255) / 256;
+    int gx = (slide_w / 4 + 255) / 256;  // four pixels per thread on the aligned path (the byte path strides)
     if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
     long long gy = yhi - ylo;
     if (gy > 16384) gy = 16384;          // the kernel strides over the rows: no 65535-row limit on the slide
     dim3 grid(gx, (unsigned)gy);

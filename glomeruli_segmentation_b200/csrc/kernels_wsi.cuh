@@ -87,30 +87,52 @@ __global__ void __launch_bounds__(256) stitch_grid_kernel(unsigned char* __restr
     const int ylo = max(row0 * sy, out_y0);
     const int yhi = min(min(min(row1 * sy + win_y, SH), y_limit), out_y0 + out_rows);
     const size_t tile_sz = (size_t)win_x * win_y;
+    // max over the resident tiles that cover slide pixel (x, y); -1 if none does
+    auto gather = [&](int x, int y, int j_lo, int j_hi) {
+        const int i_hi = min(x / sx, n_x - 1);
+        int i_lo = (x - win_x + sx) / sx;
+        if (x - win_x + 1 <= 0) i_lo = 0;
+        int best = -1;
+        for (int j = j_lo; j <= j_hi; ++j) {
+            const int ty = y - j * sy;
+            if (ty < 0 || ty >= win_y) continue;
+            for (int i = i_lo; i <= i_hi; ++i) {
+                const int tx = x - i * sx;
+                const int k = j * n_x + i;
+                if (tx < 0 || tx >= win_x || k < k0 || k >= k1) continue;
+                best = max(best, (int)tiles[(size_t)(k - k0) * tile_sz + (size_t)ty * win_x + tx]);
+            }
+        }
+        return best;
+    };
+    // four pixels per thread and one 32-bit store when rows are 4-byte aligned (always for a multi-GPU band written over NVLink:
+    // a warp then stores 128 contiguous bytes instead of 32); byte stores otherwise
+    const bool vec4 = (SW % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
     for (int y = ylo + blockIdx.y; y < yhi; y += gridDim.y) {
         const int j_hi = min(min(y / sy, n_y - 1), row1);
         int j_lo = (y - win_y + sy) / sy;                 // ceil((y - win_y + 1) / sy) for y-win_y+1 > 0
         if (y - win_y + 1 <= 0) j_lo = 0;
         j_lo = max(j_lo, row0);
-        for (int x = blockIdx.x * 256 + threadIdx.x; x < SW; x += gridDim.x * 256) {
-            const int i_hi = min(x / sx, n_x - 1);
-            int i_lo = (x - win_x + sx) / sx;
-            if (x - win_x + 1 <= 0) i_lo = 0;
-            int best = -1;
-            for (int j = j_lo; j <= j_hi; ++j) {
-                const int ty = y - j * sy;
-                if (ty < 0 || ty >= win_y) continue;
-                for (int i = i_lo; i <= i_hi; ++i) {
-                    const int tx = x - i * sx;
-                    const int k = j * n_x + i;
-                    if (tx < 0 || tx >= win_x || k < k0 || k >= k1) continue;
-                    const int v = tiles[(size_t)(k - k0) * tile_sz + (size_t)ty * win_x + tx];
-                    best = max(best, v);
+        unsigned char* drow = out + (size_t)(y - out_y0) * SW;
+        if (vec4) {
+            for (int x = 4 * (blockIdx.x * 256 + threadIdx.x); x < SW; x += 4 * gridDim.x * 256) {
+                int b[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) b[q] = gather(x + q, y, j_lo, j_hi);
+                unsigned int* d = reinterpret_cast<unsigned int*>(drow + x);
+                if (overwrite) {
+                    *d = (unsigned)max(b[0], 0) | ((unsigned)max(b[1], 0) << 8) | ((unsigned)max(b[2], 0) << 16) | ((unsigned)max(b[3], 0) << 24);
+                } else if ((b[0] & b[1] & b[2] & b[3]) >= 0) {      // at least one of the four pixels is covered (b = -1 otherwise)
+                    const unsigned int cand = (unsigned)max(b[0], 0) | ((unsigned)max(b[1], 0) << 8) | ((unsigned)max(b[2], 0) << 16) | ((unsigned)max(b[3], 0) << 24);
+                    *d = __vmaxu4(*d, cand);
                 }
             }
-            unsigned char* d = out + (size_t)(y - out_y0) * SW + x;
-            if (overwrite) *d = (unsigned char)max(best, 0);
-            else if (best >= 0) *d = (unsigned char)max((int)*d, best);
+        } else {
+            for (int x = blockIdx.x * 256 + threadIdx.x; x < SW; x += gridDim.x * 256) {
+                const int best = gather(x, y, j_lo, j_hi);
+                if (overwrite) drow[x] = (unsigned char)max(best, 0);
+                else if (best >= 0) drow[x] = (unsigned char)max((int)drow[x], best);
+            }
         }
     }
 }
