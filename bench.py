@@ -35,6 +35,15 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries the JSON line and nothing else: libraries that write to fd 1 (NCCL prints its version there) go to stderr.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 HBM_FALLBACK_GBS = 6650.0           # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal CUDA-core fp32 roof
 FLOP_PER_CROP_FULL = 3.636e9
@@ -199,7 +208,7 @@ def run_reference(args):
                          "sample": "%d synthetic 512x512 crops per step, oracle port of Model.py on torch %s CPU" % (sample, torch.__version__)},
         "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(workload, batch):
@@ -664,7 +673,7 @@ def run_ours(args):
     if args.workload == "wsi":
         line = measure_wsi(ctx, args, args.steps, max(args.warmup, 1))
         if ctx.rank == 0:
-            print(json.dumps(line))
+            emit(line)
         ctx.close()
         return
     wl = args.workload or "espnet_c_b64_fp32"
@@ -727,7 +736,7 @@ def run_ours(args):
                                           % (cpu_sample, cpu_dt, torch.__version__)}
     if extra:
         line["configs"] = extra
-    print(json.dumps(line))
+    emit(line)
     ctx.close()
 
 
