@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -32,6 +33,9 @@ static thread_local std::string g_create_error;
 #define LAUNCH_COUNT() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 namespace {
+
+// kernel classes of the "pdl" option
+constexpr int kPdlStem = 1, kPdlPool = 2, kPdlDown = 4, kPdlBranch = 8, kPdlReduce = 16, kPdlTail = 32, kPdlLast = 64, kPdlAll = 127;
 
 struct HostTensor {
     const float* data;
@@ -93,6 +97,8 @@ struct espnet_handle {
     int down_impl = 1;     // tensor-core 3x3-s2 reduce: 1 = TMA-staged input regions (default), 0 = per-thread global loads ("down_impl")
     int tail_impl = 0;     // 1 = run the generic run-time-class-count tail kernels even for 5 / 20 classes ("tail_impl", cross-check)
     int dec_impl = 1;      // decoder tail: 1 = 4 pixels per thread (dec_c4_kernel), 0 = 1 pixel per thread ("dec_impl")
+    int pdl = -1;          // programmatic dependent launch between the kernels of a forward (kernels_fp32.cuh): -1 auto, else a kPdl* mask
+    int pdl_eff = 0;       // the mask of the forward being enqueued
     int l2_reverse = 1;    // 1x1 reduce walks its tiles against the order of the kernel that produced its input (L2 reuse)
     int tc_reduce = 1;     // f16tc mode: 1 = 1x1 reduce on tensor cores, 0 = CUDA-core fp32 reduce rounded to fp16 ("tc_reduce")
     int branch_impl = 0;   // 0 auto, 1 per-thread global loads, 2 TMA-staged (espnet_set_option "branch_impl")
@@ -159,6 +165,37 @@ struct ProfScope {
         h->prof.push_back({name, e0, e1});
     }
 };
+
+inline bool pdl_on(const espnet_t* h, int cls) { return (h->pdl_eff & cls) && !h->profiling; }
+
+// "pdl" = -1: measured on B200 (profiles/r02_pdl_ab.json), full ESPNet, 512 x 512 crops: chaining the kernels takes 16 % off a
+// batch-1 forward (0.340 -> 0.285 ms) and 3 % off batch 16, nothing at batch 64 -- and a chain that is never broken (every kernel
+// of every forward, back to back) costs 15 % there.  So: small forwards chain everything but the stem, large ones nothing.
+constexpr long long kPdlAutoPixels = 32LL * 512 * 512;
+inline int pdl_mask_for(const espnet_t* h, long long pixels) {
+    if (h->pdl >= 0) return h->pdl;
+    return pixels <= kPdlAutoPixels ? (kPdlAll & ~kPdlStem) : 0;
+}
+
+// A persistent kernel (one CTA per SM, static tile split) launched that way must not fit twice on an SM: its CTAs are placed
+// as SMs drain, and the SMs that drain first would take two of them while others stay empty.
+constexpr size_t kOneCtaSmem = 116 * 1024;
+inline size_t one_cta_smem(size_t bytes) { return bytes > kOneCtaSmem ? bytes : kOneCtaSmem; }
+
+// Launch of a forward kernel that follows the pdl_trigger / pdl_wait contract (kernels_fp32.cuh): with the "pdl" option on
+// (default) its CTAs may be scheduled while the kernel before it drains.  Off while profiling: the per-kernel events would
+// otherwise time overlapping prologues.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(espnet_t* h, int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_on(h, cls) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ----------------------------------------------------------------------------------------------
 // packing
@@ -582,13 +619,13 @@ template <int CIN, int NOUT, int NKC, bool SPLIT = false>
 int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h, int B, int H, int W, cudaStream_t st) {
     using Cfg = ReduceTcCfg<CIN, NOUT, SPLIT>;
     const int HW = H * W;
-    int rc = set_smem(h, reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT>, Cfg::SMEM);
+    int rc = set_smem(h, reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT>, one_cta_smem(Cfg::SMEM));
     if (rc) return rc;
     const int grid = grid_for(h, (long long)B * ((HW + 127) / 128));
     { ProfScope _ps(h, SPLIT ? (CIN == 64 ? "reduce1x1_tc3_l2" : "reduce1x1_tc3_l3") : (CIN == 64 ? "reduce1x1_tc_l2" : "reduce1x1_tc_l3"), st);
       // the producer of `in` (a branch kernel) wrote its tiles in ascending order: walking them in DESCENDING order starts on
       // the part that is still in the 126 MB L2 ("l2_reverse" option, default on)
-      reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kRedThreads, Cfg::SMEM, st>>>(in, reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1)), o1h, B, HW, h->l2_reverse); }
+      launch_k(h, kPdlReduce, reduce1x1_tc_kernel<CIN, NOUT, NKC, SPLIT>, grid, kRedThreads, one_cta_smem(Cfg::SMEM), st, in, reinterpret_cast<const __half*>(h->dparams_h + (SPLIT ? bw.tc3_c1 : bw.tc_c1)), o1h, B, HW, h->l2_reverse); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -618,22 +655,22 @@ int run_reduce3x3_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
     // TMA needs 16 B row pitches and a 16 B aligned base; "down_impl" = 0 forces the per-thread loader kernel (cross-check)
     if (h->down_impl != 0 && (Wi % 4) == 0 && ((uintptr_t)in % 16) == 0) {
         using TCfg = DownTmaCfg<CIN, NOUT, SPLIT>;
-        int rc = set_smem(h, reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT>, TCfg::SMEM);
+        int rc = set_smem(h, reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT>, one_cta_smem(TCfg::SMEM));
         if (rc) return rc;
         CUtensorMap map, map_tail;
         rc = make_down_map(h, &map, in, B, CIN, Hi, Wi, 16);
         if (rc) return rc;
         rc = make_down_map(h, &map_tail, in, B, CIN, Hi, Wi, (CIN % 16) ? (CIN % 16) : 16);     // the last K step's real channels only
         if (rc) return rc;
-        { ProfScope _ps(h, name, st); reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, TCfg::SMEM, st>>>(map, map_tail, wp, o1h, B, Hi, Wi); }
+        { ProfScope _ps(h, name, st); launch_k(h, kPdlDown, reduce3x3s2_tma_kernel<CIN, NOUT, NKC, SPLIT>, grid, kDownThreads, one_cta_smem(TCfg::SMEM), st, map, map_tail, wp, o1h, B, Hi, Wi); }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         return ESPNET_OK;
     }
     using Cfg = DownTcCfg<CIN, NOUT, SPLIT>;
-    int rc = set_smem(h, reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT>, Cfg::SMEM);
+    int rc = set_smem(h, reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT>, one_cta_smem(Cfg::SMEM));
     if (rc) return rc;
-    { ProfScope _ps(h, name, st); reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT><<<grid, kDownThreads, Cfg::SMEM, st>>>(in, wp, o1h, B, Hi, Wi); }
+    { ProfScope _ps(h, name, st); launch_k(h, kPdlDown, reduce3x3s2_tc_kernel<CIN, NOUT, NKC, SPLIT>, grid, kDownThreads, one_cta_smem(Cfg::SMEM), st, in, wp, o1h, B, Hi, Wi); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -675,11 +712,11 @@ int run_branch_tc(espnet_t* h, const BlockW& bw, const __half* o1h, const float*
     auto k1 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 1, SPLIT>;
     auto k2 = esp_branch_tc_kernel<NKC, NOUT, CO1, CO, 2, SPLIT>;
     auto kern = var == 0 ? k0 : (var == 1 ? k1 : k2);
-    rc = set_smem(h, kern, Cfg::SMEM);
+    rc = set_smem(h, kern, one_cta_smem(Cfg::SMEM));
     if (rc) return rc;
     const int grid = grid_for(h, tiles);
     { ProfScope _ps(h, SPLIT ? (NKC == 2 ? "esp_branch_tc3_l2" : "esp_branch_tc3_l3") : (NKC == 2 ? "esp_branch_tc_l2" : "esp_branch_tc_l3"), st);
-      kern<<<grid, kTcThreads, Cfg::SMEM, st>>>(map, p); }
+      launch_k(h, kPdlBranch, kern, grid, kTcThreads, one_cta_smem(Cfg::SMEM), st, map, p); }
     LAUNCH_COUNT();
     CUDA_TRY(h, cudaPeekAtLastError());
     return ESPNET_OK;
@@ -712,7 +749,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
             int g4 = (int)((n / 4 + 255) / 256);
             if (g4 > 8 * h->num_sms) g4 = 8 * h->num_sms;
             if (g4 < 1) g4 = 1;
-            { ProfScope _ps(h, "head3", st); head3v_kernel<NC><<<g4, 256, 0, st>>>(p); }
+            { ProfScope _ps(h, "head3", st); launch_k(h, kPdlTail, head3v_kernel<NC>, g4, 256, 0, st, p); }
         } else {
             { ProfScope _ps(h, "head3", st); head3_kernel<NC><<<grid, 256, 0, st>>>(p); }
         }
@@ -722,7 +759,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
             h->stages["encoder.classifier"] = {p.enc_out, (size_t)B * NC * H8 * W8};
             if (a->mask) {
                 dim3 g((W / 4 + 31) / 32, (H + 7) / 8, B);     // one thread = 4 output pixels
-                { ProfScope _ps(h, "upsample8_argmax", st); upsample8_argmax_kernel<NC><<<g, 256, 0, st>>>(p.enc_out, B, H8, W8, a->mask, nullptr); }
+                { ProfScope _ps(h, "upsample8_argmax", st); launch_k(h, kPdlLast, upsample8_argmax_kernel<NC>, g, 256, 0, st, (const float*)p.enc_out, B, H8, W8, a->mask, (float*)nullptr); }
                 LAUNCH_COUNT();
                 CUDA_TRY(h, cudaPeekAtLastError());
             }
@@ -742,7 +779,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
             int g4 = (int)((n / 4 + 255) / 256);
             if (g4 > 8 * h->num_sms) g4 = 8 * h->num_sms;
             if (g4 < 1) g4 = 1;
-            { ProfScope _ps(h, "dec_a", st); dec_av_kernel<NC><<<g4, 256, 0, st>>>(p); }
+            { ProfScope _ps(h, "dec_a", st); launch_k(h, kPdlTail, dec_av_kernel<NC>, g4, 256, 0, st, p); }
         } else {
             { ProfScope _ps(h, "dec_a", st); dec_a_kernel<NC><<<grid, 256, 0, st>>>(p); }
         }
@@ -764,7 +801,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         const bool b4 = NC == 5 && h->dec_impl != 0 && (W4 % 4 == 0) && (((uintptr_t)p.tin | (uintptr_t)p.comb) % 16 == 0);
         if (b4) {
             dim3 g4((W4 / 4 + 31) / 32, (H4 + 7) / 8, B);
-            { ProfScope _ps(h, "dec_b", st); dec_b4_kernel<NC><<<g4, 256, 0, st>>>(p); }
+            { ProfScope _ps(h, "dec_b", st); launch_k(h, kPdlTail, dec_b4_kernel<NC>, g4, 256, 0, st, p); }
         } else {
             ProfScope _ps(h, "dec_b", st); dec_b_kernel<NC><<<grid, 256, 0, st>>>(p);
         }
@@ -784,7 +821,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         const bool vec_ok = NC == 5 && (W2 % 4 == 0) && (((uintptr_t)p.logits | (uintptr_t)p.prob_acc) % 16 == 0) && ((uintptr_t)p.mask % 8 == 0);
         if (vec_ok && h->dec_impl != 0) {
             dim3 g((W2 / 4 + 31) / 32, (H2 + 7) / 8, B);
-            { ProfScope _ps(h, "dec_c", st); dec_c4_kernel<NC><<<g, 256, 0, st>>>(p); }
+            { ProfScope _ps(h, "dec_c", st); launch_k(h, kPdlLast, dec_c4_kernel<NC>, g, 256, 0, st, p); }
         } else {
             dim3 g((W2 + 31) / 32, (H2 + 7) / 8, B);
             { ProfScope _ps(h, "dec_c", st); dec_c_kernel<NC><<<g, 256, 0, st>>>(p); }
@@ -907,6 +944,7 @@ int espnet_create(int classes, int p, int q, int net, int device, espnet_t** out
     espnet_t* h = new espnet_t();
     h->classes = classes; h->p = p; h->q = q; h->net = net; h->device = device;
     h->num_sms = prop.multiProcessorCount;
+    if (const char* e = std::getenv("ESPNET_B200_PDL")) { const int v = std::atoi(e); h->pdl = v < 0 ? -1 : (v & kPdlAll); }   // default of the "pdl" option
     {
         DeviceGuard g(device);
         e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
@@ -950,6 +988,7 @@ int espnet_set_option(espnet_t* h, const char* key, int value) {
     }
     if (std::strcmp(key, "down_impl") == 0 && value >= 0 && value <= 1) { h->down_impl = value; return ESPNET_OK; }
     if (std::strcmp(key, "tail_impl") == 0 && value >= 0 && value <= 1) { h->tail_impl = value; return ESPNET_OK; }
+    if (std::strcmp(key, "pdl") == 0 && value >= -1 && value <= kPdlAll) { h->pdl = value; return ESPNET_OK; }
     if (std::strcmp(key, "l2_reverse") == 0 && value >= 0 && value <= 1) { h->l2_reverse = value; return ESPNET_OK; }
     if (std::strcmp(key, "tc_reduce") == 0 && value >= 0 && value <= 2) { h->tc_reduce = value; return ESPNET_OK; }
     return fail(h, ESPNET_EINVAL, std::string("espnet_set_option: unknown option or bad value: ") + key);
@@ -1055,6 +1094,7 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
                                       "(use set_option(\"fp32_impl\", 0) or tile the crop)");
 
     DeviceGuard g(h->device);
+    h->pdl_eff = pdl_mask_for(h, (long long)a->B * a->H * a->W);
     cudaStream_t st = (cudaStream_t)a->stream;
     float* ws = (float*)a->workspace;
     const float* P = h->dparams;
@@ -1079,16 +1119,16 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
         dim3 grid((W2 + kStemTW - 1) / kStemTW, (H2 + kStemTH - 1) / kStemTH, B);
         {
             ProfScope _ps(h, "stem", st);
-            if (a->in_fmt == 0) stem_kernel<0><<<grid, 256, 0, st>>>(p);
-            else if (a->in_fmt == 1) stem_kernel<1><<<grid, 256, 0, st>>>(p);
-            else stem_kernel<2><<<grid, 256, 0, st>>>(p);
+            if (a->in_fmt == 0) launch_k(h, kPdlStem, stem_kernel<0>, grid, 256, 0, st, p);
+            else if (a->in_fmt == 1) launch_k(h, kPdlStem, stem_kernel<1>, grid, 256, 0, st, p);
+            else launch_k(h, kPdlStem, stem_kernel<2>, grid, 256, 0, st, p);
         }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         const size_t n = (size_t)B * 3 * H4 * W4;
         int g2 = (int)((n + 255) / 256);
         if (g2 > 8 * h->num_sms) g2 = 8 * h->num_sms;
-        { ProfScope _ps(h, "pool_b2", st); pool_b2_kernel<<<g2, 256, 0, st>>>(ws + L.inp1raw, B, H2, W2, P + pk.b2_s, P + pk.b2_t, P + pk.b2_a, ws + L.out1cat, 131, 128); }
+        { ProfScope _ps(h, "pool_b2", st); launch_k(h, kPdlPool, pool_b2_kernel, g2, 256, 0, st, (const float*)(ws + L.inp1raw), B, H2, W2, P + pk.b2_s, P + pk.b2_t, P + pk.b2_a, ws + L.out1cat, 131, 128); }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         h->stages["b1"] = {ws + L.out0cat, (size_t)B * 19 * H2 * W2};

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) dec_c4_kernel(const DecCParams<NC> p) {
     __shared__ __align__(16) float sw[CI * 3 * WR];
     __shared__ float swt[NC * NC * 4];
     __shared__ float sb[3 * NC];
+    pdl_trigger();
     for (int i = threadIdx.x; i < CI * 3 * WR; i += 256) {
         const int r = i / WR, k = i - r * WR;
         sw[i] = k < 3 * NC ? p.w[r * 3 * NC + k] : 0.f;
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(256) dec_c4_kernel(const DecCParams<NC> p) {
     for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
     for (int i = threadIdx.x; i < NC; i += 256) { sb[i] = p.s[i]; sb[NC + i] = p.t[i]; sb[2 * NC + i] = p.a[i]; }
     __syncthreads();
+    pdl_wait();
     const int H2 = p.H2, W2 = p.W2;
     const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -164,12 +166,14 @@ __global__ void __launch_bounds__(256) head3v_kernel(const Head3Params<NC> p) {
     __shared__ float sw[256 * NC];
     __shared__ float swt[NC * NC * 4];
     __shared__ float sbn[2 * NC];
+    pdl_trigger();
     for (int i = threadIdx.x; i < 256 * NC; i += 256) sw[i] = p.w[i];
     if (p.up_out) {
         for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
         for (int i = threadIdx.x; i < NC; i += 256) { sbn[i] = p.bn_s[i]; sbn[NC + i] = p.bn_t[i]; }
     }
     __syncthreads();
+    pdl_wait();
     const size_t plane = (size_t)p.H8 * p.W8;
     const size_t n4 = (size_t)p.B * plane / 4;
     for (size_t i4 = (size_t)blockIdx.x * 256 + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * 256) {
@@ -230,9 +234,11 @@ template <int NC>
 __global__ void __launch_bounds__(256) dec_av_kernel(const DecAParams<NC> p) {
     __shared__ float sw[131 * NC];
     __shared__ float sb[6 * NC];
+    pdl_trigger();
     for (int i = threadIdx.x; i < 131 * NC; i += 256) sw[i] = p.w[i];
     for (int i = threadIdx.x; i < 2 * NC; i += 256) { sb[i] = p.s[i]; sb[2 * NC + i] = p.t[i]; sb[4 * NC + i] = p.a[i]; }
     __syncthreads();
+    pdl_wait();
     const size_t plane = (size_t)p.H4 * p.W4;
     const size_t n4 = (size_t)p.B * plane / 4;
     for (size_t i4 = (size_t)blockIdx.x * 256 + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * 256) {
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(256) dec_b4_kernel(const DecBParams<NC> p) {
     __shared__ __align__(16) float sw[CI * 3 * WR];
     __shared__ float swt[NC * NC * 4];
     __shared__ float sb[6 * NC];
+    pdl_trigger();
     for (int i = threadIdx.x; i < CI * 3 * WR; i += 256) {
         const int r = i / WR, k = i - r * WR;
         sw[i] = k < 3 * NC ? p.w[r * 3 * NC + k] : 0.f;
@@ -292,6 +299,7 @@ __global__ void __launch_bounds__(256) dec_b4_kernel(const DecBParams<NC> p) {
         sb[3 * NC + i] = p.s2[i]; sb[4 * NC + i] = p.t2[i]; sb[5 * NC + i] = p.a2[i];
     }
     __syncthreads();
+    pdl_wait();
     const int H4 = p.H4, W4 = p.W4;
     const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);

@@ -36,6 +36,20 @@ constexpr int kHeavyThreads = ESPNET_HEAVY_THREADS;   // reduce3x3 / branch kern
 template <int V>
 struct IntTag { static constexpr int value = V; };
 
+// Programmatic dependent launch.  The kernels of one forward are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (espnet_api.cu: launch_k): a kernel's CTAs may become resident
+// while the kernel before it in the stream is still draining.  Contract for every kernel launched that way:
+//   * pdl_trigger() first thing (all threads), so that the kernel AFTER it may be scheduled as soon as every CTA of
+//     this one has started;
+//   * before pdl_wait() only immutable data is touched (packed weights, BN tables, tensor maps) and nothing is
+//     written to global memory: barrier init, TMEM allocation, weight staging;
+//   * pdl_wait() returns when the kernel before it has completed and its writes are visible; since that kernel
+//     did not finish its own pdl_wait() before ITS predecessor completed, everything after the waits is ordered exactly
+//     as in a plain stream.
+// Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float bn_prelu(float v, float s, float t, float a) {
     v = fmaf(v, s, t);
     return v >= 0.f ? v : a * v;
@@ -118,6 +132,7 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
     __shared__ float se[3][kStemRH][kStemPE];      // region columns 0, 2, 4, ..
     __shared__ float so[3][kStemRH][kStemPO];      // region columns 1, 3, 5, ..
     const int tid = threadIdx.x;
+    pdl_trigger();
     for (int i = tid; i < 27 * 16; i += 256) sw[i] = p.w1[i];
     for (int i = tid; i < 16; i += 256) { sp[i] = p.l1_s[i]; sp[16 + i] = p.l1_t[i]; sp[32 + i] = p.l1_a[i]; }
     for (int i = tid; i < 19; i += 256) { sp[48 + i] = p.b1_s[i]; sp[67 + i] = p.b1_t[i]; sp[86 + i] = p.b1_a[i]; }
@@ -129,6 +144,7 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
         }
     }
     __syncthreads();
+    pdl_wait();
     const int H2 = p.H >> 1, W2 = p.W >> 1;
     const int b = blockIdx.z;
     const int ry0 = 2 * (int)blockIdx.y * kStemTH - 1, rx0 = 2 * (int)blockIdx.x * kStemTW - 1;   // region origin in the crop
@@ -254,6 +270,8 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
 __global__ void __launch_bounds__(256) pool_b2_kernel(const float* __restrict__ inp1raw, int B, int H2, int W2,
                                                       const float* __restrict__ s, const float* __restrict__ t,
                                                       const float* __restrict__ a, float* __restrict__ out1cat, int C1, int ch_off) {
+    pdl_trigger();
+    pdl_wait();
     const int H4 = H2 >> 1, W4 = W2 >> 1;
     const size_t n = (size_t)B * 3 * H4 * W4;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
@@ -991,6 +1009,8 @@ __global__ void __launch_bounds__(256) dec_c_kernel(const DecCParams<NC> p) {
 template <int NC>
 __global__ void __launch_bounds__(256) upsample8_argmax_kernel(const float* __restrict__ enc, int B, int H8, int W8,
                                                                unsigned char* __restrict__ mask, float* __restrict__ up_logits) {
+    pdl_trigger();
+    pdl_wait();
     const int H = 8 * H8, W = 8 * W8;
     const int xg = 4 * (blockIdx.x * 32 + (threadIdx.x & 31));
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);

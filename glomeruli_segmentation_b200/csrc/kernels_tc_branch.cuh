@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
     const int total_tiles = p.B * tiles_x * tiles_y;
     const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+    pdl_trigger();
     if (tid == 0) {
         if ((tc::smem_addr(abuf) & 127u) != 0) __trap();   // TMA destination alignment
         tc::mbar_init(a_full + 0, 1); tc::mbar_init(a_full + 1, 1);
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) esp_branch_tc_kernel(const __gr
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above touched only weights / barriers / TMEM; the input of the kernel before is read below
 
     if (warp == 0) {
         // ===== producer =====

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
     const int total_tiles = B * tiles_x * tiles_y;
     const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+    pdl_trigger();
     if (tid == 0) {
         for (int s = 0; s < kDownStages; ++s) { tc::mbar_init(a_full + s, SPLIT ? 9 : 8); tc::mbar_init(a_empty + s, 1); }   // 8 loader warps (+ the weight producer)
         for (int s = 0; s < 2; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, 4); }
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tc_kernel(const f
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above touched only weights / barriers / TMEM; the input of the kernel before is read below
 
     if (warp == 0) {
         if (lane == 0) {
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const 
     const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int total = my_tiles * KS;
 
+    pdl_trigger();
     if (tid == 0) {
         if ((tc::smem_addr(stg) & 127u) != 0) __trap();   // TMA destination alignment
         for (int s = 0; s < NST; ++s) { tc::mbar_init(a_full + s, SPLIT ? 9 : 8); tc::mbar_init(a_empty + s, 1); }
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(kDownThreads, 1) reduce3x3s2_tma_kernel(const 
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above touched only weights / barriers / TMEM; the input of the kernel before is read below
 
     if (warp == 0) {
         // ===== TMA producer: one 33 x 20 x 16-channel fp32 box per K step into the staging ring =====

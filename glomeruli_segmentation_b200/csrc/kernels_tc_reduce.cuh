@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
     const int total_tiles = B * chunks;
     const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+    pdl_trigger();
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(a_full + s, 8); tc::mbar_init(a_empty + s, 1);
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) reduce1x1_tc_kernel(const floa
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above touched only weights / barriers / TMEM; the input of the kernel before is read below
 
     if (warp == 20) {
         // ===== MMA issuer: converged warp, one elected lane issues (tc_common.cuh: elect_one) =====

@@ -467,3 +467,36 @@ def test_generic_tail_is_bit_identical_to_the_specialised_scalar_tail(fold_sd, n
         assert torch.equal(ma, mb)
     else:       # the generic x8 up-sampler evaluates the same bilinear formula per pixel instead of per 4-pixel group
         assert (ma != mb).sum().item() <= 1e-4 * ma.numel()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16tc"])
+@pytest.mark.parametrize("net", ["full", "encoder"])
+def test_programmatic_dependent_launch_never_changes_a_result(fold_sd, net, mode):
+    """"pdl" option: every kernel of the forward may become resident while the one before it drains (it waits before touching
+    activations).  Off, automatic, every class on and two partial masks give bit-identical logits and masks, plain launches
+    and graph replay, also when forwards follow each other back to back on one stream (the next stem behind the last kernel)."""
+    from glomeruli_segmentation_b200 import ESPNet_Encoder
+    sd = fold_sd(3)
+    mean, std = FOLD_MEAN_STD[3]
+    if net == "full":
+        m = ESPNet(5, 2, 8); m.load_state_dict(sd, strict=True)
+    else:
+        m = ESPNet_Encoder(5, 2, 8); m.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    m = m.to(DEV).eval().set_mode(mode)
+    u8 = torch.from_numpy(O.synth_crops("D2", 3, 264, 200, seed=9, sigma=3.0)).to(DEV)
+    shape = (3, 5, 264, 200) if net == "full" else (3, 5, 33, 25)
+    want_lg = torch.empty(shape, device=DEV)
+    m.set_option("pdl", 0)
+    want = m.segment(u8, mean, std, logits=want_lg).clone()
+    for mask in (-1, 127, 126, 56, 7):
+        m.set_option("pdl", mask)
+        lg = [torch.empty(shape, device=DEV) for _ in range(4)]
+        got = [m.segment(u8, mean, std, logits=lg[i]) for i in range(4)]          # four forwards enqueued back to back
+        for i in range(4):
+            assert torch.equal(got[i], want) and torch.equal(lg[i], want_lg), (mask, i)
+        g = m.capture(3, 264, 200, mean, std, want_logits=True)
+        for _ in range(3):
+            g.run(u8)
+        assert torch.equal(g.mask, want) and torch.equal(g.logits, want_lg), mask
+    with pytest.raises(RuntimeError):
+        m.set_option("pdl", 128)
