@@ -302,11 +302,14 @@ def _cpu_grid_stitch(sw, sh, grid, tiles, row0, rows, y_limit):
     return out
 
 
-def test_band_buffers_and_overlap_merge_equal_the_single_pass():
+@pytest.mark.parametrize("sw,ov", [(515, 0.3), (640, 0.5), (1000, 0.25)])
+def test_band_buffers_and_overlap_merge_equal_the_single_pass(sw, ov):
     """What a multi-GPU run does per rank (wsi.segment_slide): stitch ONLY the band's rows into a band-sized buffer, then the
-    bands are placed / their overlap rows max-merged (espnet_max_merge_u8) -- emulated on one GPU for 3 'ranks'."""
-    sw, sh, ws = 515, 1389, 80
-    grid = wsi.tile_grid(sw, sh, 96, 1.0, 1.0, 0.3, 1.0)
+    bands are placed / their overlap rows max-merged (espnet_max_merge_u8) -- emulated on one GPU for 3 'ranks'.  Widths and
+    overlaps cover the byte path (width 515) and the aligned 32-bit-load path (width, window and stride all multiples of 4:
+    640 at stride 48, 1000 at stride 72); the four-pixel path with unaligned tiles is test_stitch_grid_bit_exact's (1000, 86)."""
+    sh, ws = 1389, 80
+    grid = wsi.tile_grid(sw, sh, 96, 1.0, 1.0, ov, 1.0)
     rng = np.random.default_rng(5)
     tiles = rng.integers(0, 5, (grid.count, grid.win_y, grid.win_x)).astype(np.uint8)
     d_tiles = torch.from_numpy(tiles).to(DEV)
