@@ -35,14 +35,23 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# stdout carries the JSON line and nothing else: libraries that write to fd 1 (NCCL prints its version there) go to stderr.
-_JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries the JSON line and nothing else: whatever libraries write to fd 1 (NCCL prints its version there) goes to
+    stderr from here on.  Called by main() only -- importing this module must not touch the file descriptors."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line):
-    _JSON_OUT.write(json.dumps(line) + "\n")
-    _JSON_OUT.flush()
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 HBM_FALLBACK_GBS = 6650.0           # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal CUDA-core fp32 roof (SURVEY.md 8(d))
@@ -761,6 +770,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--single-mode", action="store_true", help="skip the second leg that times the other compute mode")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
