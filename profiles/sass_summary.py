@@ -10,7 +10,7 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "glomeruli_segmentation_b200", "csrc", "libespnet_b200.so")
-MNEM = ["UTCHMMA", "A_KEEP", "A_REUSE", "LDTM", "UTMALDG", "UBLKCP", "UTMACCTL", "SYNCS", "HMMA", "FFMA2", "FFMA", "LDG", "STG", "LDS", "STS", "ATOM", "RED"]
+MNEM = ["UTCHMMA", "A_KEEP", "A_REUSE", "LDTM", "UTMALDG", "UBLKCP", "UTMACCTL", "SYNCS", "ACQBULK", "PREEXIT", "HMMA", "FFMA2", "FFMA", "LDG", "STG", "LDS", "STS", "ATOM", "RED"]
 
 
 def main():
@@ -37,7 +37,7 @@ def main():
     dem = subprocess.run(["cu++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     print("# SASS mnemonic counts per kernel of %s (architectures in the fatbin: %s)" % (os.path.relpath(SO, ROOT), ", ".join(arch)))
     print("# UTCHMMA = tcgen05.mma (.A_KEEP / .A_REUSE = A-collector pairs), LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor (TMA), UBLKCP = cp.async.bulk,")
-    print("# SYNCS = mbarrier, HMMA = legacy mma.sync (none expected), FFMA2 = packed fp32x2 FMA")
+    print("# SYNCS = mbarrier, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents (programmatic dependent launch), HMMA = legacy mma.sync (none expected), FFMA2 = packed fp32x2 FMA")
     cols = ["instr"] + MNEM
     print("%-86s " % "kernel" + " ".join("%8s" % c for c in cols))
     tot = {c: 0 for c in cols}
