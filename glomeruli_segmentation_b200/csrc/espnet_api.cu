@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -109,6 +110,7 @@ struct espnet_handle {
     // captured forwards (espnet_graph_capture): fixed buffers, one cudaGraphLaunch per forward
     struct GraphRec { cudaGraphExec_t exec = nullptr; };
     std::vector<GraphRec> graphs;
+    std::map<std::array<uint64_t, 9>, CUtensorMap> tmaps;   // encoded tensor maps by (kind, base, shape, box): a pure function of the key
     std::set<const void*> smem_done;   // kernels whose dynamic shared-memory limit has been raised on this device
     // host-convenience path (espnet_segment_host)
     cudaStream_t own_stream = nullptr;
@@ -525,6 +527,21 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // fp32 tensor map over o1 [B][N][H][Wp] with a [1][CH][64][64] box, zero OOB fill, no swizzle
+// Encoded tensor maps are cached in the handle: a descriptor is a pure function of (base address, shape, box), a forward at
+// an unchanged workspace re-uses all 16 of its maps instead of paying cuTensorMapEncodeTiled per launch (batch-1 loop).
+inline bool tmap_lookup(espnet_t* h, const std::array<uint64_t, 9>& key, CUtensorMap* map) {
+    if (!h) return false;
+    auto it = h->tmaps.find(key);
+    if (it == h->tmaps.end()) return false;
+    *map = it->second;
+    return true;
+}
+inline void tmap_store(espnet_t* h, const std::array<uint64_t, 9>& key, const CUtensorMap* map) {
+    if (!h) return;
+    if (h->tmaps.size() >= 512) h->tmaps.clear();      // callers that keep changing workspaces / shapes: bounded
+    h->tmaps[key] = *map;
+}
+
 int make_o1_map(espnet_t* h, CUtensorMap* map, const float* o1, int B, int N, int H, int W, int Wp, int CH) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -588,6 +605,8 @@ int run_branch(espnet_t* h, const BlockW& bw, const float* o1, const float* res,
 // a box row is one contiguous 768 B run (a 16 B innermost box dimension makes TMA crawl); box {48*4, 48, NKC, 1},
 // zero OOB fill (= the conv zero padding), no swizzle
 int make_o1h_map(espnet_t* h, CUtensorMap* map, const __half* o1h, int B, int NKC, int H, int W, int box_w, int box_h, int box_planes) {
+    const std::array<uint64_t, 9> key = {1, (uint64_t)(uintptr_t)o1h, (uint64_t)B, (uint64_t)NKC, (uint64_t)H, (uint64_t)W, (uint64_t)box_w, (uint64_t)box_h, (uint64_t)box_planes};
+    if (tmap_lookup(h, key, map)) return ESPNET_OK;
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)NKC, (cuuint64_t)B};
@@ -597,6 +616,7 @@ int make_o1h_map(espnet_t* h, CUtensorMap* map, const __half* o1h, int B, int NK
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)o1h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled (o1h) failed with CUresult " + std::to_string((int)r));
+    tmap_store(h, key, map);
     return ESPNET_OK;
 }
 
@@ -634,6 +654,8 @@ int run_reduce1x1_tc(espnet_t* h, const float* in, const BlockW& bw, __half* o1h
 // fp32 tensor map over a planar activation tensor [B][C][H][W] with a {20 cols, 33 rows, 16 channels, 1} box (zero OOB fill):
 // the input region of one K = 16 step of the TMA-staged 3x3-s2 reduce (kernels_tc_down.cuh)
 int make_down_map(espnet_t* h, CUtensorMap* map, const float* in, int B, int C, int H, int W, int box_c) {
+    const std::array<uint64_t, 9> key = {2, (uint64_t)(uintptr_t)in, (uint64_t)B, (uint64_t)C, (uint64_t)H, (uint64_t)W, (uint64_t)box_c, 0, 0};
+    if (tmap_lookup(h, key, map)) return ESPNET_OK;
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
@@ -643,6 +665,7 @@ int make_down_map(espnet_t* h, CUtensorMap* map, const float* in, int B, int C, 
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, ESPNET_ECUDA, "cuTensorMapEncodeTiled (3x3-s2 input) failed with CUresult " + std::to_string((int)r));
+    tmap_store(h, key, map);
     return ESPNET_OK;
 }
 
