@@ -36,7 +36,7 @@ static thread_local std::string g_create_error;
 namespace {
 
 // kernel classes of the "pdl" option
-constexpr int kPdlStem = 1, kPdlPool = 2, kPdlDown = 4, kPdlBranch = 8, kPdlReduce = 16, kPdlTail = 32, kPdlLast = 64, kPdlAll = 127;
+constexpr int kPdlStem = 1, /* 2: unused */ kPdlDown = 4, kPdlBranch = 8, kPdlReduce = 16, kPdlTail = 32, kPdlLast = 64, kPdlAll = 127;
 
 struct HostTensor {
     const float* data;
@@ -72,7 +72,7 @@ struct Packed {
 };
 
 struct Workspace {
-    size_t inp1raw, out0cat, o1, l2a, l2b, out1cat, l3a, l3b, out2cat, enc, up3, t10, comb, total;
+    size_t out0cat, o1, l2a, l2b, out1cat, l3a, l3b, out2cat, enc, up3, t10, comb, total;
 };
 
 struct StageRef {
@@ -441,7 +441,6 @@ Workspace layout(const espnet_t* h, int B, int H, int W) {
     const size_t NC = (size_t)h->classes;
     size_t off = 0;
     auto take = [&](size_t elems) { const size_t o = off; off = align_up(off + elems, 64); return o; };
-    w.inp1raw = take((size_t)B * 3 * P2);
     w.out0cat = take((size_t)B * 19 * P2);
     {   // o1 rows are padded to a multiple of 4 floats so that the map can be a TMA tensor (16 B strides)
         const size_t p4 = (size_t)(H / 4) * (size_t)pad4(W / 4), p8 = (size_t)(H / 8) * (size_t)pad4(W / 8);
@@ -1138,7 +1137,8 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
         p.w1 = P + pk.w1;
         p.l1_s = P + pk.l1_s; p.l1_t = P + pk.l1_t; p.l1_a = P + pk.l1_a;
         p.b1_s = P + pk.b1_s; p.b1_t = P + pk.b1_t; p.b1_a = P + pk.b1_a;
-        p.out0cat = ws + L.out0cat; p.inp1raw = ws + L.inp1raw;
+        p.b2_s = P + pk.b2_s; p.b2_t = P + pk.b2_t; p.b2_a = P + pk.b2_a;
+        p.out0cat = ws + L.out0cat; p.out1cat = ws + L.out1cat;
         dim3 grid((W2 + kStemTW - 1) / kStemTW, (H2 + kStemTH - 1) / kStemTH, B);
         {
             ProfScope _ps(h, "stem", st);
@@ -1146,12 +1146,6 @@ int espnet_forward(espnet_t* h, const espnet_forward_args* a) {
             else if (a->in_fmt == 1) launch_k(h, kPdlStem, stem_kernel<1>, grid, 256, 0, st, p);
             else launch_k(h, kPdlStem, stem_kernel<2>, grid, 256, 0, st, p);
         }
-        LAUNCH_COUNT();
-        CUDA_TRY(h, cudaPeekAtLastError());
-        const size_t n = (size_t)B * 3 * H4 * W4;
-        int g2 = (int)((n + 255) / 256);
-        if (g2 > 8 * h->num_sms) g2 = 8 * h->num_sms;
-        { ProfScope _ps(h, "pool_b2", st); launch_k(h, kPdlPool, pool_b2_kernel, g2, 256, 0, st, (const float*)(ws + L.inp1raw), B, H2, W2, P + pk.b2_s, P + pk.b2_t, P + pk.b2_a, ws + L.out1cat, 131, 128); }
         LAUNCH_COUNT();
         CUDA_TRY(h, cudaPeekAtLastError());
         h->stages["b1"] = {ws + L.out0cat, (size_t)B * 19 * H2 * W2};

@@ -112,17 +112,24 @@ struct StemParams {
     const float* w1;                    // [27][16]: (ci*9 + ky*3 + kx) x co
     const float *l1_s, *l1_t, *l1_a;    // level1 BN scale/shift, PReLU slope (16)
     const float *b1_s, *b1_t, *b1_a;    // b1 (19)
+    const float *b2_s, *b2_t, *b2_a;    // b2 (131): channels 128..130 = the twice-pooled image (Model.py:255,348,359)
     float* out0cat;
-    float* inp1raw;
+    float* out1cat;                     // [B,131,H/4,W/4]: this kernel writes channels 128..130
 };
 
 // Block = 32 x 16 outputs (thread: column lane, rows ty and ty + 8).  The 65 x 33 input region is staged ONCE in shared
 // memory, already normalised (u8 inputs go through a 3 x 256 table built with the reference's three separate fp32
 // roundings, so the 54 divisions per output of a direct evaluation disappear), split by column parity so that the
 // stride-2 window reads of a warp are bank-conflict free.  Accumulation order (channel, then tap) is fixed.
+//
+// sample2's SECOND AvgPool2d(3,2,1) + b2's BR on cat channels 128..130 (Model.py:255,348,359) ride along: the block's 16 x 8
+// quarter-resolution outputs need the once-pooled image on its 32 x 16 tile plus one halo row above and one halo column to
+// the left, i.e. an input region that starts two rows / columns earlier (67 x 35 instead of 65 x 33).  The once-pooled tile
+// goes through shared memory; the halo values are computed by the same 9-term sum in the same order as the neighbouring
+// block computes them, so the result is bit-identical to pooling a stored tensor (which no longer exists in HBM).
 constexpr int kStemTW = 32, kStemTH = 16;
-constexpr int kStemRW = 2 * kStemTW + 1, kStemRH = 2 * kStemTH + 1;      // 65 x 33 input region
-constexpr int kStemPE = 33, kStemPO = 32;                               // even / odd column counts
+constexpr int kStemRW = 2 * kStemTW + 3, kStemRH = 2 * kStemTH + 3;      // 67 x 35 input region, origin (2 x0 - 3, 2 y0 - 3)
+constexpr int kStemPE = 34, kStemPO = 33;                               // even / odd column counts
 
 template <int FMT>
 __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
@@ -131,6 +138,7 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
     __shared__ float lut[FMT == 0 ? 1 : 3 * 256];
     __shared__ float se[3][kStemRH][kStemPE];      // region columns 0, 2, 4, ..
     __shared__ float so[3][kStemRH][kStemPO];      // region columns 1, 3, 5, ..
+    __shared__ float sp1[3][kStemTH + 1][kStemTW + 1];   // once-pooled image: [0] = halo row / column
     const int tid = threadIdx.x;
     pdl_trigger();
     for (int i = tid; i < 27 * 16; i += 256) sw[i] = p.w1[i];
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
     pdl_wait();
     const int H2 = p.H >> 1, W2 = p.W >> 1;
     const int b = blockIdx.z;
-    const int ry0 = 2 * (int)blockIdx.y * kStemTH - 1, rx0 = 2 * (int)blockIdx.x * kStemTW - 1;   // region origin in the crop
+    const int ry0 = 2 * (int)blockIdx.y * kStemTH - 3, rx0 = 2 * (int)blockIdx.x * kStemTW - 3;   // region origin in the crop
 
     auto put = [&](int c, int r, int j, float v) {
         if (j & 1) so[c][r][j >> 1] = v; else se[c][r][j >> 1] = v;
@@ -226,9 +234,9 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const int ky = t / 3, kx = t % 3;
-            // region column 2 lane + kx: kx = 0, 2 even (index lane, lane + 1), kx = 1 odd (index lane)
-            const float a0 = kx == 1 ? so[c][2 * ty + ky][lane] : se[c][2 * ty + ky][lane + (kx >> 1)];
-            const float a1 = kx == 1 ? so[c][2 * (ty + 8) + ky][lane] : se[c][2 * (ty + 8) + ky][lane + (kx >> 1)];
+            // region column 2 lane + 2 + kx: kx = 0, 2 even (index lane + 1, lane + 2), kx = 1 odd (index lane + 1)
+            const float a0 = kx == 1 ? so[c][2 * ty + 2 + ky][lane + 1] : se[c][2 * ty + 2 + ky][lane + 1 + (kx >> 1)];
+            const float a1 = kx == 1 ? so[c][2 * (ty + 8) + 2 + ky][lane + 1] : se[c][2 * (ty + 8) + 2 + ky][lane + 1 + (kx >> 1)];
             s0 += a0; s1 += a1;
             const float4* w4 = reinterpret_cast<const float4*>(sw + (c * 9 + t) * 16);
 #pragma unroll
@@ -242,6 +250,47 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
         }
         pool[0][c] = s0 / 9.f;                                            // count_include_pad: always / 9
         pool[1][c] = s1 / 9.f;
+        sp1[c][1 + ty][1 + lane] = pool[0][c];
+        sp1[c][1 + ty + 8][1 + lane] = pool[1][c];
+    }
+    // halo of the once-pooled tile: row y2 = y0 - 1 (33 values incl. the corner) and column x2 = x0 - 1 (16 values) per channel
+    if (tid < 3 * 49) {
+        const int c = tid / 49, hh = tid - 49 * c;
+        const int hy = hh < 33 ? 0 : hh - 32, hx = hh < 33 ? hh : 0;
+        const int y2 = (int)blockIdx.y * kStemTH - 1 + hy, xh = (int)blockIdx.x * kStemTW - 1 + hx;
+        float s = 0.f;
+        if (y2 >= 0 && xh >= 0) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int r = 2 * hy + t / 3, j = 2 * hx + t % 3;
+                s += (j & 1) ? so[c][r][j >> 1] : se[c][r][j >> 1];
+            }
+            s = s / 9.f;
+        }
+        sp1[c][hy][hx] = s;
+    }
+    __syncthreads();
+    // second pool + b2 BR: 3 channels x 8 x 16 quarter-resolution outputs per block; taps outside the half-resolution image are
+    // skipped exactly like the zero padding of AvgPool2d (the divisor stays 9)
+    {
+        const int H4 = H2 >> 1, W4 = W2 >> 1;
+        for (int it = tid; it < 3 * (kStemTH / 2) * (kStemTW / 2); it += 256) {
+            const int c = it / ((kStemTH / 2) * (kStemTW / 2));
+            const int yl = (it / (kStemTW / 2)) % (kStemTH / 2), xl = it % (kStemTW / 2);
+            const int y4 = (int)blockIdx.y * (kStemTH / 2) + yl, x4 = (int)blockIdx.x * (kStemTW / 2) + xl;
+            if (y4 >= H4 || x4 >= W4) continue;
+            float sum = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int yy = 2 * y4 - 1 + ky, xx = 2 * x4 - 1 + kx;
+                    if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) sum += sp1[c][2 * yl + ky][2 * xl + kx];
+                }
+            sum = sum / 9.f;
+            const int ch = 128 + c;
+            p.out1cat[((size_t)b * 131 + ch) * H4 * W4 + (size_t)y4 * W4 + x4] = bn_prelu(sum, p.b2_s[ch], p.b2_t[ch], p.b2_a[ch]);
+        }
     }
     if (x2 >= W2) return;
     const size_t plane = (size_t)H2 * W2;
@@ -260,39 +309,11 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float s = pool[r][c];
-            p.inp1raw[(size_t)(b * 3 + c) * plane + pix] = s;
             o[(size_t)(16 + c) * plane] = bn_prelu(s, sp[48 + 16 + c], sp[67 + 16 + c], sp[86 + 16 + c]);
         }
     }
 }
 
-// sample2's second AvgPool2d(3,2,1) (Model.py:255,348) fused with b2's BR on cat channels 128..130.
-__global__ void __launch_bounds__(256) pool_b2_kernel(const float* __restrict__ inp1raw, int B, int H2, int W2,
-                                                      const float* __restrict__ s, const float* __restrict__ t,
-                                                      const float* __restrict__ a, float* __restrict__ out1cat, int C1, int ch_off) {
-    pdl_trigger();
-    pdl_wait();
-    const int H4 = H2 >> 1, W4 = W2 >> 1;
-    const size_t n = (size_t)B * 3 * H4 * W4;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const int x = (int)(i % W4);
-        const int y = (int)((i / W4) % H4);
-        const int c = (int)((i / ((size_t)W4 * H4)) % 3);
-        const int b = (int)(i / ((size_t)W4 * H4 * 3));
-        const float* src = inp1raw + (size_t)(b * 3 + c) * H2 * W2;
-        float sum = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int yy = 2 * y - 1 + ky, xx = 2 * x - 1 + kx;
-                if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) sum += __ldg(src + (size_t)yy * W2 + xx);
-            }
-        sum = sum / 9.f;
-        const int ch = ch_off + c;
-        out1cat[((size_t)b * C1 + ch) * H4 * W4 + (size_t)y * W4 + x] = bn_prelu(sum, s[ch], t[ch], a[ch]);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Work decomposition shared by the reduce / branch kernels: item = (crop, 4-row strip, 32-column

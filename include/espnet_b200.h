@@ -103,7 +103,7 @@ ESPNET_API int espnet_set_mode(espnet_t* h, int mode);            /* ESPNET_MODE
  * classes; bit-identical to the scalar specialised ones); "pdl" (programmatic dependent launch: a kernel of the
  * forward sets up its barriers / tensor memory / weights while the one before it drains and waits for it before touching
  * activations; results are identical.  -1 (default) = automatic: on for forwards of at most 32 x 512 x 512 pixels, where launch
- * gaps matter (batch 1: -16 %), off above; 0 = off; otherwise a bit mask of kernel classes: 1 stem, 2 pool_b2, 4 3x3-s2
+ * gaps matter (batch 1: -16 %), off above; 0 = off; otherwise a bit mask of kernel classes: 1 stem, 2 (unused), 4 3x3-s2
  * reduce, 8 branch, 16 1x1 reduce, 32 head / decoder, 64 last kernel.  The environment variable ESPNET_B200_PDL sets the
  * default of a new handle). */
 ESPNET_API int espnet_set_option(espnet_t* h, const char* key, int value);

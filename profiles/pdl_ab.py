@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the "pdl" option (programmatic dependent launch between the kernels of a forward), per kernel class.
-usage: python profiles/pdl_ab.py [mask ...]      masks: bit 1 stem, 2 pool_b2, 4 3x3-s2 reduce, 8 branch, 16 1x1 reduce, 32 head / decoder,
+usage: python profiles/pdl_ab.py [mask ...]      masks: bit 1 stem, 2 unused (was pool_b2, now part of the stem), 4 3x3-s2 reduce, 8 branch, 16 1x1 reduce, 32 head / decoder,
                                                  64 last kernel of the forward; PDL_AB_FAST=1: batch 64 only
 Prints one JSON record: per mask the CUDA-event time of the ESPNet-C and full ESPNet forwards at batch 64 (fp32-equivalent mode,
 inputs resident, 30 forwards back to back) and of one full forward at batch 1, plain launches and CUDA-graph replay."""
