@@ -157,64 +157,90 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
     const int b = blockIdx.z;
     const int ry0 = 2 * (int)blockIdx.y * kStemTH - 3, rx0 = 2 * (int)blockIdx.x * kStemTW - 3;   // region origin in the crop
 
-    auto put = [&](int c, int r, int j, float v) {
-        if (j & 1) so[c][r][j >> 1] = v; else se[c][r][j >> 1] = v;
-    };
     if (FMT == 0) {
+        // One warp per region row (rows w, w + 8, ..), lanes on columns lane + 32 k.  Everything that depends only on the
+        // column -- bounds test, source offset, the parity-split destination -- is computed once per thread; the loops over
+        // channel and row are fully unrolled so that row addresses are immediate offsets (the staging used to be a third of
+        // the kernel's instructions).  Asynchronous 4-byte copies, all in flight at once; src-size 0 = zero fill = conv / pool
+        // zero padding of the NORMALISED tensor (Model.py:20,230).
         const float* x = reinterpret_cast<const float*>(p.x);
-        for (int row = tid >> 5; row < 3 * kStemRH; row += 8) {      // one warp per (channel, region row)
-            const int c = row / kStemRH, r = row - c * kStemRH;
+        const int ln = tid & 31, wp = tid >> 5;
+        const uint32_t pitch = (ln & 1) ? kStemPO * 4u : kStemPE * 4u;           // bytes per region row of this lane's parity
+        const uint32_t dbase = (uint32_t)__cvta_generic_to_shared((ln & 1) ? &so[0][0][0] : &se[0][0][0]) + (uint32_t)(ln >> 1) * 4u;
+        bool cok[3];
+        int xoff[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int xx = rx0 + ln + 32 * k;
+            cok[k] = ln + 32 * k < kStemRW && xx >= 0 && xx < p.W;
+            xoff[k] = cok[k] ? xx : 0;
+        }
+        const size_t cplane = (size_t)p.H * p.W;
+        const float* xb = x + (size_t)b * 3 * cplane;
+#pragma unroll
+        for (int i = 0; i < (kStemRH + 7) / 8; ++i) {
+            const int r = wp + 8 * i;
+            if (r >= kStemRH) break;                                             // warp-uniform
             const int yy = ry0 + r;
             const bool row_ok = yy >= 0 && yy < p.H;
-            const float* xr = x + ((size_t)(b * 3 + c) * p.H + (row_ok ? yy : 0)) * p.W;
+            const float* xr = xb + (size_t)(row_ok ? yy : 0) * p.W;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int j = (tid & 31) + 32 * k;
-                if (j >= kStemRW) continue;
-                const int xx = rx0 + j;
-                // asynchronous 4-byte copies (all of a warp's rows in flight at once); src-size 0 = zero fill =
-                // conv / pool zero padding of the NORMALISED tensor (Model.py:20,230)
-                const bool ok = row_ok && xx >= 0 && xx < p.W;
-                float* dst = (j & 1) ? &so[c][r][j >> 1] : &se[c][r][j >> 1];
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
-                             "l"(ok ? xr + xx : x), "r"(ok ? 4 : 0) : "memory");
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t drow = dbase + (uint32_t)(c * kStemRH + r) * pitch;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (32 * k >= kStemRW) continue;
+                    if (32 * (k + 1) > kStemRW && ln + 32 * k >= kStemRW) continue;
+                    const bool ok = row_ok && cok[k];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + 64u * k),
+                                 "l"(ok ? xr + c * cplane + xoff[k] : x), "r"(ok ? 4 : 0) : "memory");
+                }
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
-        // u8 HWC: one task = one region pixel (3 consecutive bytes, a warp reads 96 contiguous bytes per load); all byte
-        // loads of a thread are issued first (phase 1), then table look-ups and the parity-split stores (phase 2)
+        // u8 HWC: one thread = one region column and every third region row (3 x 67 = 201 of the 256 threads); a warp still reads
+        // consecutive pixels of a row (96 contiguous bytes per load instruction).  Column tests, the source column and the
+        // parity-split destination are per-thread constants; all byte loads of a thread are issued first (phase 1), then the
+        // table look-ups and stores (phase 2).
         const unsigned char* x = reinterpret_cast<const unsigned char*>(p.x);
         long long ox = 0, oy = 0, pitch_px = p.W, rows = p.H, row0 = (long long)b * p.H;
         if (FMT == 2) { ox = p.origins[2 * b]; oy = p.origins[2 * b + 1]; pitch_px = p.slide_w; rows = p.slide_h; row0 = 0; }
-        constexpr int kPix = kStemRH * kStemRW, kIters = (kPix + 255) / 256;
-        unsigned int bgr[kIters];        // b | g << 8 | r << 16, bit 24 = pixel is inside the crop (else zero padding)
+        constexpr int kPh = 3, kPer = (kStemRH + kPh - 1) / kPh;
+        const int ph = tid >= 2 * kStemRW ? 2 : (tid >= kStemRW ? 1 : 0);
+        const int j = tid - ph * kStemRW;
+        const bool active = tid < kPh * kStemRW;
+        const int xx = rx0 + j;
+        const long long sx = ox + xx;
+        const bool col_in_crop = active && xx >= 0 && xx < p.W;
+        const bool col_in_src = sx >= 0 && sx < pitch_px;           // outside the slide openslide pads with 0 (then normalised like any pixel)
+        const unsigned char* qcol = x + (col_in_src ? sx : 0) * 3;
+        unsigned int bgr[kPer];          // b | g << 8 | r << 16, bit 24 = pixel is inside the crop (else zero padding)
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-            const int t = tid + 256 * i;
-            const int r = t / kStemRW, j = t - r * kStemRW;
-            const int yy = ry0 + r, xx = rx0 + j;
+        for (int i = 0; i < kPer; ++i) {
+            const int r = ph + kPh * i;
+            const int yy = ry0 + r;
             unsigned int u = 0;
-            if (t < kPix && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+            if (r < kStemRH && col_in_crop && yy >= 0 && yy < p.H) {
                 u = 1u << 24;
-                const long long sy = oy + yy, sx = ox + xx;
-                // outside the slide openslide pads with 0 (then normalised like any pixel)
-                if (sy >= 0 && sy < rows && sx >= 0 && sx < pitch_px) {
-                    const unsigned char* q = x + ((row0 + sy) * pitch_px + sx) * 3;
+                const long long sy = oy + yy;
+                if (col_in_src && sy >= 0 && sy < rows) {
+                    const unsigned char* q = qcol + (row0 + sy) * pitch_px * 3;
                     u |= (unsigned int)__ldg(q) | ((unsigned int)__ldg(q + 1) << 8) | ((unsigned int)__ldg(q + 2) << 16);
                 }
             }
             bgr[i] = u;
         }
+        float* dcol = (j & 1) ? &so[0][0][j >> 1] : &se[0][0][j >> 1];
+        const int dpitch = (j & 1) ? kStemPO : kStemPE;
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-            const int t = tid + 256 * i;
-            if (t >= kPix) continue;
-            const int r = t / kStemRW, j = t - r * kStemRW;
+        for (int i = 0; i < kPer; ++i) {
+            const int r = ph + kPh * i;
+            if (!active || r >= kStemRH) continue;
             const unsigned int u = bgr[i];
             const bool in_crop = (u >> 24) != 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) put(c, r, j, in_crop ? lut[c * 256 + ((u >> (8 * c)) & 255u)] : 0.f);
+            for (int c = 0; c < 3; ++c) dcol[(c * kStemRH + r) * dpitch] = in_crop ? lut[c * 256 + ((u >> (8 * c)) & 255u)] : 0.f;
         }
     }
     __syncthreads();
@@ -272,24 +298,27 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
     __syncthreads();
     // second pool + b2 BR: 3 channels x 8 x 16 quarter-resolution outputs per block; taps outside the half-resolution image are
     // skipped exactly like the zero padding of AvgPool2d (the divisor stays 9)
-    {
+    if (tid < (kStemTH / 2) * (kStemTW / 2)) {
         const int H4 = H2 >> 1, W4 = W2 >> 1;
-        for (int it = tid; it < 3 * (kStemTH / 2) * (kStemTW / 2); it += 256) {
-            const int c = it / ((kStemTH / 2) * (kStemTW / 2));
-            const int yl = (it / (kStemTW / 2)) % (kStemTH / 2), xl = it % (kStemTW / 2);
-            const int y4 = (int)blockIdx.y * (kStemTH / 2) + yl, x4 = (int)blockIdx.x * (kStemTW / 2) + xl;
-            if (y4 >= H4 || x4 >= W4) continue;
-            float sum = 0.f;
+        const int yl = tid / (kStemTW / 2), xl = tid % (kStemTW / 2);
+        const int y4 = (int)blockIdx.y * (kStemTH / 2) + yl, x4 = (int)blockIdx.x * (kStemTW / 2) + xl;
+        if (y4 < H4 && x4 < W4) {
+            bool ok[9];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+            for (int t = 0; t < 9; ++t) {
+                const int yy = 2 * y4 - 1 + t / 3, xx = 2 * x4 - 1 + t % 3;
+                ok[t] = yy >= 0 && yy < H2 && xx >= 0 && xx < W2;
+            }
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int yy = 2 * y4 - 1 + ky, xx = 2 * x4 - 1 + kx;
-                    if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) sum += sp1[c][2 * yl + ky][2 * xl + kx];
-                }
-            sum = sum / 9.f;
-            const int ch = 128 + c;
-            p.out1cat[((size_t)b * 131 + ch) * H4 * W4 + (size_t)y4 * W4 + x4] = bn_prelu(sum, p.b2_s[ch], p.b2_t[ch], p.b2_a[ch]);
+            for (int c = 0; c < 3; ++c) {
+                float sum = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
+                    if (ok[t]) sum += sp1[c][2 * yl + t / 3][2 * xl + t % 3];
+                sum = sum / 9.f;
+                const int ch = 128 + c;
+                p.out1cat[((size_t)b * 131 + ch) * H4 * W4 + (size_t)y4 * W4 + x4] = bn_prelu(sum, p.b2_s[ch], p.b2_t[ch], p.b2_a[ch]);
+            }
         }
     }
     if (x2 >= W2) return;
