@@ -414,6 +414,10 @@ def measure_crops(ctx, args, wl, mode, B, steps, warmup, sampler=None, want_othe
     l0 = _lib.lib().espnet_launch_count()
     ms = ctx.timed(step_resident, steps)
     launches = int(_lib.lib().espnet_launch_count() - l0)
+    # per-kernel CUDA events on the same stream, straight after the timed steps (same thermal state as `value`)
+    rep, kernels = (None, None)
+    if want_profile:
+        rep, kernels = profile_kernels(model, step_resident, min(steps, 5))
     for _ in range(warmup):
         step_e2e()
     if pipe is not None:
@@ -426,9 +430,8 @@ def measure_crops(ctx, args, wl, mode, B, steps, warmup, sampler=None, want_othe
                    "api": ("model.host_pipeline(depth=%d).submit(pinned host u8 crops, pinned host u8 masks): H2D, fused normalise + forward + arg-max, "
                            "D2H every step on 3 streams" % args.depth) if pipe is not None else
                           "u8_host.to(device) -> ESPNetEnsemble.segment (5 forwards, softmax accumulate, arg-max) -> mask_host.copy_(), one stream"}}
-    rep = None
     if want_profile:
-        rep, out["kernels"] = profile_kernels(model, step_resident, min(steps, 5))
+        out["kernels"] = kernels
         out["top_kernel"] = max(rep, key=lambda k: rep[k][0]) if rep else None
     if ens is not None:
         # per-fold mask agreement of the reduced-precision mode with the fp32-equivalent mode on this batch (D1: the hard input)

@@ -780,7 +780,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         if (!full) {
             h->stages["encoder.classifier"] = {p.enc_out, (size_t)B * NC * H8 * W8};
             if (a->mask) {
-                dim3 g((W / 4 + 31) / 32, (H + 7) / 8, B);     // one thread = 4 output pixels
+                dim3 g((W / 4 + 31) / 32, (H8 + 1 + 7) / 8, B);     // one thread = 4 output pixels x the 8 rows of a source-row pair
                 { ProfScope _ps(h, "upsample8_argmax", st); launch_k(h, kPdlLast, upsample8_argmax_kernel<NC>, g, 256, 0, st, (const float*)p.enc_out, B, H8, W8, a->mask, (float*)nullptr); }
                 LAUNCH_COUNT();
                 CUDA_TRY(h, cudaPeekAtLastError());

@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
     const int b = blockIdx.z;
     const int ry0 = 2 * (int)blockIdx.y * kStemTH - 3, rx0 = 2 * (int)blockIdx.x * kStemTW - 3;   // region origin in the crop
 
+    auto put = [&](int c, int r, int j, float v) {
+        if (j & 1) so[c][r][j >> 1] = v; else se[c][r][j >> 1] = v;
+    };
     if (FMT == 0) {
         // One warp per region row (rows w, w + 8, ..), lanes on columns lane + 32 k.  Everything that depends only on the
         // column -- bounds test, source offset, the parity-split destination -- is computed once per thread; the loops over
@@ -199,48 +202,41 @@ __global__ void __launch_bounds__(256, 4) stem_kernel(const StemParams p) {
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
-        // u8 HWC: one thread = one region column and every third region row (3 x 67 = 201 of the 256 threads); a warp still reads
-        // consecutive pixels of a row (96 contiguous bytes per load instruction).  Column tests, the source column and the
-        // parity-split destination are per-thread constants; all byte loads of a thread are issued first (phase 1), then the
-        // table look-ups and stores (phase 2).
+        // u8 HWC: one task = one region pixel (3 consecutive bytes, a warp reads 96 contiguous bytes per load); all byte
+        // loads of a thread are issued first (phase 1), then table look-ups and the parity-split stores (phase 2).  This phase
+        // is bound by the latency of the byte loads, not by instruction count: a column-per-thread mapping with half the index
+        // arithmetic but 12 instead of 10 pixels per thread (201 of 256 threads busy) was 12 % SLOWER (ncu: 226 -> 253 us).
         const unsigned char* x = reinterpret_cast<const unsigned char*>(p.x);
         long long ox = 0, oy = 0, pitch_px = p.W, rows = p.H, row0 = (long long)b * p.H;
         if (FMT == 2) { ox = p.origins[2 * b]; oy = p.origins[2 * b + 1]; pitch_px = p.slide_w; rows = p.slide_h; row0 = 0; }
-        constexpr int kPh = 3, kPer = (kStemRH + kPh - 1) / kPh;
-        const int ph = tid >= 2 * kStemRW ? 2 : (tid >= kStemRW ? 1 : 0);
-        const int j = tid - ph * kStemRW;
-        const bool active = tid < kPh * kStemRW;
-        const int xx = rx0 + j;
-        const long long sx = ox + xx;
-        const bool col_in_crop = active && xx >= 0 && xx < p.W;
-        const bool col_in_src = sx >= 0 && sx < pitch_px;           // outside the slide openslide pads with 0 (then normalised like any pixel)
-        const unsigned char* qcol = x + (col_in_src ? sx : 0) * 3;
-        unsigned int bgr[kPer];          // b | g << 8 | r << 16, bit 24 = pixel is inside the crop (else zero padding)
+        constexpr int kPix = kStemRH * kStemRW, kIters = (kPix + 255) / 256;
+        unsigned int bgr[kIters];        // b | g << 8 | r << 16, bit 24 = pixel is inside the crop (else zero padding)
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) {
-            const int r = ph + kPh * i;
-            const int yy = ry0 + r;
+        for (int i = 0; i < kIters; ++i) {
+            const int t = tid + 256 * i;
+            const int r = t / kStemRW, j = t - r * kStemRW;
+            const int yy = ry0 + r, xx = rx0 + j;
             unsigned int u = 0;
-            if (r < kStemRH && col_in_crop && yy >= 0 && yy < p.H) {
+            if (t < kPix && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
                 u = 1u << 24;
-                const long long sy = oy + yy;
-                if (col_in_src && sy >= 0 && sy < rows) {
-                    const unsigned char* q = qcol + (row0 + sy) * pitch_px * 3;
+                const long long sy = oy + yy, sx = ox + xx;
+                // outside the slide openslide pads with 0 (then normalised like any pixel)
+                if (sy >= 0 && sy < rows && sx >= 0 && sx < pitch_px) {
+                    const unsigned char* q = x + ((row0 + sy) * pitch_px + sx) * 3;
                     u |= (unsigned int)__ldg(q) | ((unsigned int)__ldg(q + 1) << 8) | ((unsigned int)__ldg(q + 2) << 16);
                 }
             }
             bgr[i] = u;
         }
-        float* dcol = (j & 1) ? &so[0][0][j >> 1] : &se[0][0][j >> 1];
-        const int dpitch = (j & 1) ? kStemPO : kStemPE;
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) {
-            const int r = ph + kPh * i;
-            if (!active || r >= kStemRH) continue;
+        for (int i = 0; i < kIters; ++i) {
+            const int t = tid + 256 * i;
+            if (t >= kPix) continue;
+            const int r = t / kStemRW, j = t - r * kStemRW;
             const unsigned int u = bgr[i];
             const bool in_crop = (u >> 24) != 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) dcol[(c * kStemRH + r) * dpitch] = in_crop ? lut[c * 256 + ((u >> (8 * c)) & 255u)] : 0.f;
+            for (int c = 0; c < 3; ++c) put(c, r, j, in_crop ? lut[c * 256 + ((u >> (8 * c)) & 255u)] : 0.f);
         }
     }
     __syncthreads();
@@ -1054,23 +1050,27 @@ __global__ void __launch_bounds__(256) dec_c_kernel(const DecCParams<NC> p) {
 
 // ESPNet-C tail: nn.Upsample(scale_factor=8, mode='bilinear', align_corners=False)
 // (VisualizeResults_iou.py:258-261,125-126) + arg-max (:128) of encoder logits [B,NC,H8,W8].
-// One thread = 4 horizontally adjacent output pixels (a uchar4 / float4 store): they read at most 3 source columns, which
-// are loaded once; the interpolation arithmetic per pixel is unchanged (same operations, same order).
+// One thread = 4 horizontally adjacent output pixels (a uchar4 / float4 store per row) x the 8 output rows that share the
+// same pair of source rows (row group k: output rows [8k + 4, 8k + 12), k = -1 .. H8 - 1; the first and the last group hold the 4
+// rows whose source index is clamped).  The 4 pixels read at most 3 source columns, loaded once per class; the two HORIZONTAL
+// interpolations per (pixel, class) are computed once and reused by the rows, each of which only blends them vertically and
+// updates its running arg-max (class-outer loop: registers do not grow with NC).  Same formula as torch's upsample_bilinear2d: h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11).
+// (The one-row-per-thread version of round 1 spent 130 instructions per pixel and 90 us per 64 crops of 512 x 512, issue-bound;
+// this one 51 us.)
+constexpr int kUpRows = 8;       // output rows per thread = all rows that share a source-row pair (4 rows per thread: 57 instead of 51 us)
 template <int NC>
-__global__ void __launch_bounds__(256) upsample8_argmax_kernel(const float* __restrict__ enc, int B, int H8, int W8,
+__global__ void __launch_bounds__(256, 2) upsample8_argmax_kernel(const float* __restrict__ enc, int B, int H8, int W8,
                                                                unsigned char* __restrict__ mask, float* __restrict__ up_logits) {
     pdl_trigger();
     pdl_wait();
     const int H = 8 * H8, W = 8 * W8;
     const int xg = 4 * (blockIdx.x * 32 + (threadIdx.x & 31));
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int k = (int)blockIdx.y * 8 + (int)(threadIdx.x >> 5) - 1, ybase = 8 * k + 4;
     const int b = blockIdx.z;
-    if (xg >= W || y >= H) return;
+    if (xg >= W || k >= H8) return;
     // area_pixel_compute_source_index(scale=1/8, align_corners=False): src = (dst+0.5)/8-0.5, clamped at 0
-    float sy = 0.125f * ((float)y + 0.5f) - 0.5f; sy = sy < 0.f ? 0.f : sy;
-    const int y0 = (int)sy;
+    const int y0 = k < 0 ? 0 : k;
     const int y1 = y0 + (y0 < H8 - 1 ? 1 : 0);
-    const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
     int x0[4]; float lx1[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1081,7 +1081,16 @@ __global__ void __launch_bounds__(256) upsample8_argmax_kernel(const float* __re
     // source columns c0 = x0[0], c0 + 1, c0 + 2 (clamped): x0[j] is c0 or c0 + 1, its right neighbour min(x0[j] + 1, W8 - 1)
     const int c0 = x0[0], c1 = min(c0 + 1, W8 - 1), c2 = min(c0 + 2, W8 - 1);
     const size_t plane = (size_t)H8 * W8;
-    float v[4][NC];
+    // rows of this group and their vertical weights
+    float ly1r[kUpRows];
+#pragma unroll
+    for (int r = 0; r < kUpRows; ++r) {
+        float sy = 0.125f * ((float)(ybase + r) + 0.5f) - 0.5f; sy = sy < 0.f ? 0.f : sy;
+        ly1r[r] = sy - (float)y0;
+    }
+    const bool lg_vec = (reinterpret_cast<uintptr_t>(up_logits) & 15) == 0;
+    float bv[kUpRows][4];        // running arg-max per (row, pixel): the first maximum wins, like argmax_first
+    int bi[kUpRows][4];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const float* s = enc + ((size_t)b * NC + c) * plane;
@@ -1089,25 +1098,44 @@ __global__ void __launch_bounds__(256) upsample8_argmax_kernel(const float* __re
         const float* r1 = s + (size_t)y1 * W8;
         const float a0 = __ldg(r0 + c0), a1 = __ldg(r0 + c1), a2 = __ldg(r0 + c2);
         const float b0 = __ldg(r1 + c0), b1 = __ldg(r1 + c1), b2 = __ldg(r1 + c2);
+        float t0[4], t1[4];      // horizontal interpolation on source rows y0 / y1
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool sh = x0[j] != c0;
             const float v00 = sh ? a1 : a0, v01 = sh ? a2 : a1, v10 = sh ? b1 : b0, v11 = sh ? b2 : b1;
             const float lx0 = 1.f - lx1[j];
-            v[j][c] = ly0 * (lx0 * v00 + lx1[j] * v01) + ly1 * (lx0 * v10 + lx1[j] * v11);
+            t0[j] = lx0 * v00 + lx1[j] * v01;
+            t1[j] = lx0 * v10 + lx1[j] * v11;
         }
-        if (up_logits) {
-            float* d = up_logits + ((size_t)b * NC + c) * H * W + (size_t)y * W + xg;
-            if ((reinterpret_cast<uintptr_t>(up_logits) & 15) == 0) *reinterpret_cast<float4*>(d) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
-            else { d[0] = v[0][c]; d[1] = v[1][c]; d[2] = v[2][c]; d[3] = v[3][c]; }
+#pragma unroll
+        for (int r = 0; r < kUpRows; ++r) {
+            const int y = ybase + r;
+            const float ly1 = ly1r[r], ly0 = 1.f - ly1;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = ly0 * t0[j] + ly1 * t1[j];
+                if (c == 0) { bv[r][j] = v[j]; bi[r][j] = 0; }
+                else if (v[j] > bv[r][j]) { bv[r][j] = v[j]; bi[r][j] = c; }
+            }
+            if (up_logits && y >= 0 && y < H) {
+                float* d = up_logits + ((size_t)b * NC + c) * H * W + (size_t)y * W + xg;
+                if (lg_vec) *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+                else { d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3]; }
+            }
         }
     }
     if (mask) {
-        unsigned char* d = mask + (size_t)b * H * W + (size_t)y * W + xg;
-        const uchar4 m4 = make_uchar4((unsigned char)argmax_first<NC>(v[0]), (unsigned char)argmax_first<NC>(v[1]),
-                                      (unsigned char)argmax_first<NC>(v[2]), (unsigned char)argmax_first<NC>(v[3]));
-        if ((reinterpret_cast<uintptr_t>(mask) & 3) == 0) *reinterpret_cast<uchar4*>(d) = m4;     // caller buffers may be unaligned views
-        else { d[0] = m4.x; d[1] = m4.y; d[2] = m4.z; d[3] = m4.w; }
+        const bool mk_vec = (reinterpret_cast<uintptr_t>(mask) & 3) == 0;     // caller buffers may be unaligned views
+#pragma unroll
+        for (int r = 0; r < kUpRows; ++r) {
+            const int y = ybase + r;
+            if (y < 0 || y >= H) continue;
+            unsigned char* d = mask + (size_t)b * H * W + (size_t)y * W + xg;
+            const uchar4 m4 = make_uchar4((unsigned char)bi[r][0], (unsigned char)bi[r][1], (unsigned char)bi[r][2], (unsigned char)bi[r][3]);
+            if (mk_vec) *reinterpret_cast<uchar4*>(d) = m4;
+            else { d[0] = m4.x; d[1] = m4.y; d[2] = m4.z; d[3] = m4.w; }
+        }
     }
 }
 

@@ -29,11 +29,12 @@ if net == "encoder":
     m.load_state_dict(sd, strict=True)
     m = m.to(dev).eval().set_mode(mode)
     x = (((u8.float() - torch.tensor(mean, device=dev)) / torch.tensor(std, device=dev)) / 255.0).permute(0, 3, 1, 2).contiguous()
+    y = None
     for _ in range(iters):
         y = m(x)
     mask = m.segment(u8, mean, std)
     torch.cuda.synchronize()
-    print("ok", net, mode, B, tuple(y.shape), float(y.abs().max()), int(mask.sum()))
+    print("ok", net, mode, B, None if y is None else (tuple(y.shape), float(y.abs().max())), int(mask.sum()))
 else:
     m = ESPNet(5, 2, 8)
     m.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=True)
