@@ -227,7 +227,9 @@ def workload_config(workload, batch):
         "espnet_b256_ens5": "full ESPNet (5,2,8), %d synthetic 512x512 crops per GPU per step, folds 1-5 softmax ensemble" % batch,
     }
     return {"workload": names[workload], "crop": "512x512", "batch_per_gpu": batch, "weights": "espnet_fold1 (tests/golden)",
-            "l2": "inputs (201 MB fp32 / 50 MB u8 per batch of 64) and activations (>2 GB) exceed the 126 MB L2; no flush needed"}
+            "l2": "inputs (201 MB fp32 / 50 MB u8 per batch of 64) and activations (>2 GB) exceed the 126 MB L2; no flush needed",
+            "timing": "`value` and `e2e` are separate legs: each starts from an idle GPU (1 s pause before the e2e leg), runs W warm-up steps and "
+                      "times K steps with CUDA events; `configs.sustained` is the same workload looped for >= 2.5 s under the power cap"}
 
 
 def kernel_roofline(name, per_launch_ms, B, hbm_peak, peak_src):
@@ -418,6 +420,8 @@ def measure_crops(ctx, args, wl, mode, B, steps, warmup, sampler=None, want_othe
     rep, kernels = (None, None)
     if want_profile:
         rep, kernels = profile_kernels(model, step_resident, min(steps, 5))
+    torch.cuda.synchronize()
+    time.sleep(1.0)             # the e2e leg starts like the resident leg did: idle GPU, then W warm-up steps, then K timed steps
     for _ in range(warmup):
         step_e2e()
     if pipe is not None:
