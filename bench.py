@@ -655,6 +655,7 @@ def measure_wsi(ctx, args, steps, warmup):
     ms = ctx.max_over_ranks(ms)
     fwd = ctx.max_over_ranks(tm.get("forward_ms", 0.0))
     gather_ms = ctx.max_over_ranks(tm.get("gather_ms", 0.0)) if ctx.world > 1 else 0.0
+    place_ms = ctx.max_over_ranks(tm.get("place_kernels_ms", 0.0)) if ctx.world > 1 else 0.0
     clocks = sampler.stop() if ctx.rank == 0 else None
     hist = torch.bincount(ds8.reshape(-1).long(), minlength=5).tolist() if ctx.rank == 0 else None
     if gather is not None:
@@ -672,7 +673,10 @@ def measure_wsi(ctx, args, steps, warmup):
                                "overlap strips max-merged, T4 /8 mask" % (sw, sh, args.overlap, grid.count, grid.n_x, grid.n_y),
                    "tile_batch": batch, "mode": args.mode, "l2": "slide band (%.1f GB) and tile activations exceed the 126 MB L2" % ((y1 - y0) * sw * 3 / 1e9)},
         "tiles_per_s": grid.count * steps / (ms * 1e-3), "tile_mpx_per_s": grid.count * 0.262144 * steps / (ms * 1e-3),
-        "phases_ms_max_over_ranks": {"tiles_forward": fwd, "band_gather": gather_ms, "band_gather_share": gather_ms / (ms / steps) if ms else None},
+        "phases_ms_max_over_ranks": {"tiles_forward": fwd, "band_gather": gather_ms, "band_gather_share": gather_ms / (ms / steps) if ms else None,
+                                     "band_place_kernels": place_ms,
+                                     "note": "band_gather = from the end of a rank's own tiles to the assembled mask on rank 0, i.e. it contains the wait for the "
+                                             "slowest rank and two barriers; band_place_kernels = the stitch kernels that write over NVLink, alone (p2p)"},
         "gather": gather_note, "gather_bytes_received_rank0": tm.get("bytes_received"), "gather_bytes_max_merged": tm.get("bytes_merged"),
         "gpu_launches": launches, "clocks": clocks, "ds8_class_histogram": hist,
     }

@@ -394,13 +394,17 @@ class PeerGather:
         with an earlier band); rank 0 merges the strips.  Returns byte counts."""
         y0, split, y1 = self.plan[self.rank]
         self.dist.barrier(group=self.group)          # rank 0 is done with the previous result
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         if k1 > k0 and y1 > y0:
             if split > y0:
                 _stitch_raw(self._ptr1 + self.rank * self.strip_rows * self.sw, y0, split - y0, self.sh, self.sw, tile_masks, self.grid, k0, k1, ws)
             if y1 > split:
                 _stitch_raw(self._ptr0 + split * self.sw, split, y1 - split, self.sh, self.sw, tile_masks, self.grid, k0, k1, ws)
+        ev[1].record()
         self.dist.barrier(group=self.group)          # every band has landed (kernel completion makes the peer writes visible)
-        stats = {"bytes_received": 0, "bytes_merged": 0, "gather": "p2p"}
+        # `_place_events`: the stitch kernels alone (this rank's writes into rank 0's memory), without the barriers around them
+        stats = {"bytes_received": 0, "bytes_merged": 0, "gather": "p2p", "_place_events": ev}
         if self.rank == 0:
             for r, (a, sp, b) in enumerate(self.plan):
                 if r and sp > a:
@@ -476,7 +480,10 @@ def segment_slide(model, slide_u8: torch.Tensor, mean, std, std_size: float = 51
     if ev:
         ev[3].record()
     ds8 = downsample8(level0, ws) if (level0 is not None and tuple(level0.shape) == (sh, sw)) else None
+    pe = stats.pop("_place_events", None)
     if ev:
         torch.cuda.synchronize(dev)
+        if pe is not None:
+            stats["place_kernels_ms"] = pe[0].elapsed_time(pe[1])
         timings.update(forward_ms=ev[0].elapsed_time(ev[1]), stitch_ms=ev[1].elapsed_time(ev[2]), gather_ms=ev[2].elapsed_time(ev[3]), **stats)
     return (level0 if level0 is not None else band), ds8, n_local
