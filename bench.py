@@ -499,7 +499,7 @@ def strip_private(rec):
 
 def measure_batch1(ctx, args):
     """BASELINE configs[0]: ESPNet(5,2,8) fold1, ONE 512x512 crop, forward + arg-max.  Device-timed latency of the plain
-    forward (~30 launches) and of the CUDA-graph replay (1 launch), host-to-host latency through the graph, CPU port beside."""
+    forward (29 launches) and of the CUDA-graph replay (1 launch), host-to-host latency through the graph, CPU port beside."""
     from glomeruli_segmentation_b200 import FOLD_MEAN_STD
     mean, std = FOLD_MEAN_STD[1]
     model = make_model(ctx, False, 1, "fp32", args.fp32_impl)
@@ -537,7 +537,7 @@ def measure_batch1(ctx, args):
     res["host_to_host_ms"] = ctx.max_over_ranks((time.perf_counter() - t0) / n * 1e3)
     assert torch.equal(g.mask, model.segment(u8, mean, std))
     res.update(unit="ms per 512x512 crop (batch 1)", crops_per_s_graph=1e3 / res["graph_replay_ms"],
-               note="plain = ~30 kernel launches per crop; graph = espnet_graph_launch; host_to_host = pinned H2D + graph + D2H + stream sync per crop (wall clock)")
+               note="plain = 29 kernel launches per crop (programmatically chained); graph = espnet_graph_launch; host_to_host = pinned H2D + graph + D2H + stream sync per crop (wall clock)")
     if ctx.world == 1 and not args.no_cpu:
         v, dt = time_cpu("espnet_b64_fp32", 1, 5, 2)
         res["cpu_port_ms"] = dt * 1e3

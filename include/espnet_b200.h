@@ -114,7 +114,7 @@ ESPNET_API size_t espnet_workspace_bytes(const espnet_t* h, int B, int H, int W)
 ESPNET_API int espnet_forward(espnet_t* h, const espnet_forward_args* a);
 
 /* The same forward recorded once into a CUDA graph with THESE buffers (x, outputs, workspace stay owned by the caller and must
- * stay valid and in place); espnet_graph_launch replays it on `stream` with one launch instead of ~30.  For the per-crop loop of
+ * stay valid and in place); espnet_graph_launch replays it on `stream` with one launch instead of 26 - 29.  For the per-crop loop of
  * VisualizeResults_iou.py:100-129 (batch 1), where the forward is launch-latency bound.  Repacking weights drops all graphs. */
 ESPNET_API int espnet_graph_capture(espnet_t* h, const espnet_forward_args* a, int* graph_id);
 ESPNET_API int espnet_graph_launch(espnet_t* h, int graph_id, void* stream);
