@@ -398,7 +398,7 @@ def measure_crops(ctx, args, wl, mode, B, steps, warmup, sampler=None, want_othe
             def step_resident():
                 model._engine.forward(x_dev, _lib.IN_F32_NCHW, B, H, W, logits=logits, mask=mask_dev)
                 return logits
-    pipe = model.host_pipeline(B, H, W, mean, std, depth=args.depth) if ens is None else None
+    pipe = model.host_pipeline(B, H, W, mean, std, depth=args.depth) if ens is None else ens.host_pipeline(B, H, W, depth=2)
 
     def step_e2e():
         if pipe is not None:     # public streaming API: H2D / kernels / D2H of consecutive batches overlap
@@ -432,8 +432,9 @@ def measure_crops(ctx, args, wl, mode, B, steps, warmup, sampler=None, want_othe
            "e2e": {"value": ctx.world * B * steps / (ms_e2e * 1e-3), "unit": "crops/s", "h2d_bytes_per_step": int(u8_host.numel()),
                    "d2h_bytes_per_step": int(mask_host.numel()), "ms_per_step": ms_e2e / steps,
                    "api": ("model.host_pipeline(depth=%d).submit(pinned host u8 crops, pinned host u8 masks): H2D, fused normalise + forward + arg-max, "
-                           "D2H every step on 3 streams" % args.depth) if pipe is not None else
-                          "u8_host.to(device) -> ESPNetEnsemble.segment (5 forwards, softmax accumulate, arg-max) -> mask_host.copy_(), one stream"}}
+                           "D2H every step on 3 streams" % args.depth) if ens is None else
+                          "ESPNetEnsemble.host_pipeline(depth=2).submit(pinned host u8 crops, pinned host u8 masks): H2D, 5 forwards with softmax "
+                          "accumulate + arg-max, D2H every step on 3 streams"}}
     if want_profile:
         out["kernels"] = kernels
         out["top_kernel"] = max(rep, key=lambda k: rep[k][0]) if rep else None

@@ -398,9 +398,17 @@ class HostPipeline:
     streams with `depth` device slots, so the copies of one batch overlap the kernels of its neighbours; `drain()` waits
     for everything submitted.  Host tensors must stay alive (and should be pinned) until drained."""
 
-    def __init__(self, model: "_KernelBacked", B: int, H: int, W: int, mean, std, depth: int = 2):
-        dev = model._param_device()
+    def __init__(self, model, B: int, H: int, W: int, mean, std, depth: int = 2):
+        # `model`: an ESPNet / ESPNet_Encoder (normalised with mean / std) or an ESPNetEnsemble (every fold has its own mean / std)
+        ens = isinstance(model, ESPNetEnsemble)
+        first = model.models[0] if ens else model
+        dev = first._param_device()
         self.model, self.mean, self.std, self.shape, self.depth = model, mean, std, (B, H, W), depth
+        if ens:
+            self._prob = torch.empty((B, first.classes, H, W), dtype=torch.float32, device=dev)      # shared: one run stream
+            self._run = lambda d_in, d_mask: model.segment(d_in, out=d_mask, prob=self._prob)
+        else:
+            self._run = lambda d_in, d_mask: model.segment(d_in, mean, std, out=d_mask)
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.d_in = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(depth)]
         self.d_mask = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(depth)]
@@ -408,7 +416,8 @@ class HostPipeline:
         self.ev_run = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
         self.n = 0
-        model._ready(dev)
+        for m in (model.models if ens else [model]):
+            m._ready(dev)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(torch.cuda.current_stream(dev))
 
@@ -422,7 +431,7 @@ class HostPipeline:
             self.ev_in[k].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in[k])
-            self.model.segment(self.d_in[k], self.mean, self.std, out=self.d_mask[k])
+            self._run(self.d_in[k], self.d_mask[k])
             self.ev_run[k].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_run[k])
@@ -503,12 +512,28 @@ class ESPNetEnsemble:
         assert len(models) == len(mean_std) and len(models) >= 1
         self.models, self.mean_std = list(models), list(mean_std)
 
-    def segment(self, crops_u8: torch.Tensor, return_prob: bool = False):
+    def host_pipeline(self, B: int, H: int, W: int, depth: int = 2) -> "HostPipeline":
+        """Pipelined host-to-host ensemble segmentation of a stream of batches (see HostPipeline)."""
+        return HostPipeline(self, B, H, W, None, None, depth)
+
+    def segment(self, crops_u8: torch.Tensor, return_prob: bool = False, out: Optional[torch.Tensor] = None,
+                prob: Optional[torch.Tensor] = None):
+        """`out` (uint8 [B,H,W]) and `prob` (float32 [B,classes,H,W] scratch for the accumulated softmax) may be passed in
+        to avoid the allocations."""
         crops_u8 = crops_u8.contiguous()
         B, H, W, _ = crops_u8.shape
         nc = self.models[0].classes
-        prob = torch.empty((B, nc, H, W), dtype=torch.float32, device=crops_u8.device)
-        mask = torch.empty((B, H, W), dtype=torch.uint8, device=crops_u8.device)
+        dev = crops_u8.device
+        if prob is None:
+            prob = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
+        elif prob.dtype != torch.float32 or tuple(prob.shape) != (B, nc, H, W) or prob.device != dev or not prob.is_contiguous():
+            raise RuntimeError("prob must be a contiguous float32 [B,classes,H,W] tensor on the crops' device")
+        if out is None:
+            mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        elif out.dtype != torch.uint8 or tuple(out.shape) != (B, H, W) or out.device != dev or not out.is_contiguous():
+            raise RuntimeError("out must be a contiguous uint8 [B,H,W] tensor on the crops' device")
+        else:
+            mask = out
         last = len(self.models) - 1
         for k, (m, (mean, std)) in enumerate(zip(self.models, self.mean_std)):
             eng = m._ready(crops_u8.device)

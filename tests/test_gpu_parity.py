@@ -503,3 +503,23 @@ def test_programmatic_dependent_launch_never_changes_a_result(fold_sd, net, mode
         assert torch.equal(g.mask, want) and torch.equal(g.logits, want_lg), mask
     with pytest.raises(RuntimeError):
         m.set_option("pdl", 128)
+
+
+def test_host_pipelines_match_the_resident_calls(fold_sd):
+    """HostPipeline (pinned host crops in, host masks out, copies overlapped with the kernels of neighbouring batches) for a
+    single model and for the 5-fold ensemble: every batch of a stream of different batches equals the plain segment() call."""
+    models = [_model(fold_sd(k)) for k in range(1, 6)]
+    ens = ESPNetEnsemble(models, [FOLD_MEAN_STD[k] for k in range(1, 6)])
+    mean, std = FOLD_MEAN_STD[1]
+    B, H, W = 3, 72, 104
+    batches = [torch.from_numpy(O.synth_crops("D2", B, H, W, seed=40 + i, sigma=3.0)).pin_memory() for i in range(5)]
+    for owner, plain, pipe in ((models[0], lambda d: models[0].segment(d, mean, std), models[0].host_pipeline(B, H, W, mean, std, depth=2)),
+                               (ens, lambda d: ens.segment(d), ens.host_pipeline(B, H, W, depth=2))):
+        outs = [torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in batches]
+        for u8, o in zip(batches, outs):
+            pipe.submit(u8, o)
+        pipe.drain()
+        for u8, o in zip(batches, outs):
+            assert torch.equal(o, plain(u8.to(DEV)).cpu())
+    with pytest.raises(RuntimeError):
+        ens.segment(batches[0].to(DEV), out=torch.empty((B, H, W), dtype=torch.float32, device=DEV))
