@@ -9,7 +9,8 @@
 
 namespace espnet {
 
-template <int NC>
+// UNR = input channels whose loads are in flight per thread (2 for large launches, 8 for small, latency-bound ones; same order).
+template <int NC, int UNR>
 __global__ void __launch_bounds__(256) dec_c4_kernel(const DecCParams<NC> p) {
     constexpr int CI = NC + 19;
     // weights of one (input channel, tap row): 3 kx x NC values padded to WR floats -> LDS.128 broadcasts
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(256) dec_c4_kernel(const DecCParams<NC> p) {
         const int yy = y + ky - 1;
         if (yy < 0 || yy >= H2) continue;                 // zero padding row (uniform per warp)
         const size_t roff = (size_t)yy * W2 + x0;
-#pragma unroll 2
+#pragma unroll UNR
         for (int ci = 0; ci < CI; ++ci) {
             const float* row = (ci < NC ? p.comb + ((size_t)b * NC + ci) * plane : p.out0cat + ((size_t)b * 19 + (ci - NC)) * plane) + roff;
             const float4 c = __ldg(reinterpret_cast<const float4*>(row));
@@ -161,22 +162,25 @@ namespace espnet {
 
 // S7, 4 pixels per thread (plane % 4 == 0): b3 output -> encoder.classifier 1x1 (Model.py:271,302) [+ br BN + up_l3 ConvT for
 // the full net, Model.py:331,334,370].  One 16 B load per channel plane feeds 4 x NC FMAs; same arithmetic as head3_kernel.
-template <int NC>
+// UNR = channel planes whose loads are in flight per thread: 8 for large launches (bandwidth), 32 for small ones.  Small launches
+// also use 64-thread blocks (blockDim.x is a run-time value here): at batch 1 the 1 024 threads of this kernel would otherwise sit
+// on 4 SMs and pull the whole 4 MB input through 4 SMs' L2 ports.  The summation order per pixel never changes.
+template <int NC, int UNR>
 __global__ void __launch_bounds__(256) head3v_kernel(const Head3Params<NC> p) {
     __shared__ float sw[256 * NC];
     __shared__ float swt[NC * NC * 4];
     __shared__ float sbn[2 * NC];
     pdl_trigger();
-    for (int i = threadIdx.x; i < 256 * NC; i += 256) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < 256 * NC; i += blockDim.x) sw[i] = p.w[i];
     if (p.up_out) {
-        for (int i = threadIdx.x; i < NC * NC * 4; i += 256) swt[i] = p.wt[i];
-        for (int i = threadIdx.x; i < NC; i += 256) { sbn[i] = p.bn_s[i]; sbn[NC + i] = p.bn_t[i]; }
+        for (int i = threadIdx.x; i < NC * NC * 4; i += blockDim.x) swt[i] = p.wt[i];
+        for (int i = threadIdx.x; i < NC; i += blockDim.x) { sbn[i] = p.bn_s[i]; sbn[NC + i] = p.bn_t[i]; }
     }
     __syncthreads();
     pdl_wait();
     const size_t plane = (size_t)p.H8 * p.W8;
     const size_t n4 = (size_t)p.B * plane / 4;
-    for (size_t i4 = (size_t)blockIdx.x * 256 + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * 256) {
+    for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * blockDim.x) {
         const size_t i = 4 * i4;
         const int b = (int)(i / plane);
         const size_t pix = i % plane;
@@ -186,14 +190,19 @@ __global__ void __launch_bounds__(256) head3v_kernel(const Head3Params<NC> p) {
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int j = 0; j < NC; ++j) acc[q][j] = 0.f;
-#pragma unroll 8
-        for (int ci = 0; ci < 256; ++ci) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)ci * plane));
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += UNR) {
+            float4 a[UNR];                                 // all loads of a batch first, then the FMAs in channel order
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                const float wv = sw[ci * NC + j];
-                acc[0][j] = fmaf(a.x, wv, acc[0][j]); acc[1][j] = fmaf(a.y, wv, acc[1][j]);
-                acc[2][j] = fmaf(a.z, wv, acc[2][j]); acc[3][j] = fmaf(a.w, wv, acc[3][j]);
+            for (int u = 0; u < UNR; ++u) a[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(c0 + u) * plane));
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const float wv = sw[(c0 + u) * NC + j];
+                    acc[0][j] = fmaf(a[u].x, wv, acc[0][j]); acc[1][j] = fmaf(a[u].y, wv, acc[1][j]);
+                    acc[2][j] = fmaf(a[u].z, wv, acc[2][j]); acc[3][j] = fmaf(a[u].w, wv, acc[3][j]);
+                }
             }
         }
         if (p.enc_out) {
@@ -230,18 +239,18 @@ __global__ void __launch_bounds__(256) head3v_kernel(const Head3Params<NC> p) {
 
 // S8 + first half of S9, 4 pixels per thread (plane % 4 == 0): level3_C 1x1 131->NC (Model.py:330,372), cat with up_l3's output
 // (Model.py:373), combine_l2_l3[0] BR(2NC).  Same arithmetic as dec_a_kernel.
-template <int NC>
+template <int NC, int UNR>
 __global__ void __launch_bounds__(256) dec_av_kernel(const DecAParams<NC> p) {
     __shared__ float sw[131 * NC];
     __shared__ float sb[6 * NC];
     pdl_trigger();
-    for (int i = threadIdx.x; i < 131 * NC; i += 256) sw[i] = p.w[i];
-    for (int i = threadIdx.x; i < 2 * NC; i += 256) { sb[i] = p.s[i]; sb[2 * NC + i] = p.t[i]; sb[4 * NC + i] = p.a[i]; }
+    for (int i = threadIdx.x; i < 131 * NC; i += blockDim.x) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < 2 * NC; i += blockDim.x) { sb[i] = p.s[i]; sb[2 * NC + i] = p.t[i]; sb[4 * NC + i] = p.a[i]; }
     __syncthreads();
     pdl_wait();
     const size_t plane = (size_t)p.H4 * p.W4;
     const size_t n4 = (size_t)p.B * plane / 4;
-    for (size_t i4 = (size_t)blockIdx.x * 256 + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * 256) {
+    for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * blockDim.x) {
         const size_t i = 4 * i4;
         const int b = (int)(i / plane);
         const size_t pix = i % plane;
@@ -251,14 +260,21 @@ __global__ void __launch_bounds__(256) dec_av_kernel(const DecAParams<NC> p) {
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int j = 0; j < NC; ++j) acc[q][j] = 0.f;
-#pragma unroll 8
-        for (int ci = 0; ci < 131; ++ci) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)ci * plane));
+#pragma unroll 1
+        for (int c0 = 0; c0 < 131; c0 += UNR) {
+            float4 a[UNR];                                 // all loads of a batch first, then the FMAs in channel order
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                const float wv = sw[ci * NC + j];
-                acc[0][j] = fmaf(a.x, wv, acc[0][j]); acc[1][j] = fmaf(a.y, wv, acc[1][j]);
-                acc[2][j] = fmaf(a.z, wv, acc[2][j]); acc[3][j] = fmaf(a.w, wv, acc[3][j]);
+            for (int u = 0; u < UNR; ++u)
+                a[u] = c0 + u < 131 ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(c0 + u) * plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (c0 + u >= 131) break;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const float wv = sw[(c0 + u) * NC + j];
+                    acc[0][j] = fmaf(a[u].x, wv, acc[0][j]); acc[1][j] = fmaf(a[u].y, wv, acc[1][j]);
+                    acc[2][j] = fmaf(a[u].z, wv, acc[2][j]); acc[3][j] = fmaf(a[u].w, wv, acc[3][j]);
+                }
             }
         }
         float* d = p.tout + (size_t)b * 2 * NC * plane + pix;
@@ -281,7 +297,7 @@ __global__ void __launch_bounds__(256) dec_av_kernel(const DecAParams<NC> p) {
 // (Model.py:335,374) -> comb [B,NC,H2,W2].  One thread owns FOUR consecutive quarter-resolution pixels: per (input channel,
 // tap row) 3 loads (one 16 B vector + the two neighbours) and 4 LDS.128 weight broadcasts feed 12 NC FMAs (the one-pixel
 // dec_b_kernel issues one scalar LDS per FMA and is LSU-bound), and each class row leaves as two 16 B stores.
-template <int NC>
+template <int NC, int UNR>
 __global__ void __launch_bounds__(256) dec_b4_kernel(const DecBParams<NC> p) {
     constexpr int CI = 2 * NC;
     constexpr int WR = (3 * NC + 3) & ~3;
@@ -317,7 +333,7 @@ __global__ void __launch_bounds__(256) dec_b4_kernel(const DecBParams<NC> p) {
         const int yy = y + ky - 1;
         if (yy < 0 || yy >= H4) continue;                 // zero padding row (uniform per warp)
         const float* rowb = p.tin + (size_t)b * CI * plane + (size_t)yy * W4 + x0;
-#pragma unroll 2
+#pragma unroll UNR
         for (int ci = 0; ci < CI; ++ci) {
             const float* row = rowb + (size_t)ci * plane;
             const float4 c = __ldg(reinterpret_cast<const float4*>(row));
