@@ -171,7 +171,7 @@ struct ProfScope {
 inline bool pdl_on(const espnet_t* h, int cls) { return (h->pdl_eff & cls) && !h->profiling; }
 
 // "pdl" = -1: measured on B200 (profiles/r02_pdl_ab.json), full ESPNet, 512 x 512 crops: chaining the kernels takes 16 % off a
-// batch-1 forward (0.340 -> 0.285 ms) and 3 % off batch 16, nothing at batch 64 -- and a chain that is never broken (every kernel
+// batch-1 forward (0.318 -> 0.264 ms) and 3 % off batch 16, nothing at batch 64 -- and a chain that is never broken (every kernel
 // of every forward, back to back) costs 15 % there.  So: small forwards chain everything but the stem, large ones nothing.
 constexpr long long kPdlAutoPixels = 32LL * 512 * 512;
 inline int pdl_mask_for(const espnet_t* h, long long pixels) {
