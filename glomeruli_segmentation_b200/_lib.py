@@ -90,7 +90,7 @@ def _up_to_date() -> bool:
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU; one translation unit, ~3 min).
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU; one translation unit, ~2 min).
     Like make, nothing is recompiled when the library is newer than all of its sources (force=True or
     ESPNET_B200_REBUILD=1 recompiles anyway)."""
     if not force and not os.environ.get("ESPNET_B200_REBUILD") and _up_to_date():

@@ -774,9 +774,11 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
             int g4 = (int)((n / 4 + 255) / 256);
             if (g4 > 8 * h->num_sms) g4 = 8 * h->num_sms;
             if (g4 < 1) g4 = 1;
-            { ProfScope _ps(h, "head3", st);
-              if (small_launch(h, n / 4)) launch_k(h, kPdlTail, head3v_kernel<NC, 32>, (int)((n / 4 + 63) / 64), 64, 0, st, p);
-              else launch_k(h, kPdlTail, head3v_kernel<NC, 8>, g4, 256, 0, st, p); }
+            if constexpr (NC == 5) {      // (v4 implies NC == 5: the 4-pixel kernels are only instantiated for 5 classes)
+                ProfScope _ps(h, "head3", st);
+                if (small_launch(h, n / 4)) launch_k(h, kPdlTail, head3v_kernel<NC, 32>, (int)((n / 4 + 63) / 64), 64, 0, st, p);
+                else launch_k(h, kPdlTail, head3v_kernel<NC, 8>, g4, 256, 0, st, p);
+            }
         } else {
             { ProfScope _ps(h, "head3", st); head3_kernel<NC><<<grid, 256, 0, st>>>(p); }
         }
@@ -806,9 +808,11 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
             int g4 = (int)((n / 4 + 255) / 256);
             if (g4 > 8 * h->num_sms) g4 = 8 * h->num_sms;
             if (g4 < 1) g4 = 1;
-            { ProfScope _ps(h, "dec_a", st);
-              if (small_launch(h, n / 4)) launch_k(h, kPdlTail, dec_av_kernel<NC, 32>, (int)((n / 4 + 63) / 64), 64, 0, st, p);
-              else launch_k(h, kPdlTail, dec_av_kernel<NC, 8>, g4, 256, 0, st, p); }
+            if constexpr (NC == 5) {
+                ProfScope _ps(h, "dec_a", st);
+                if (small_launch(h, n / 4)) launch_k(h, kPdlTail, dec_av_kernel<NC, 32>, (int)((n / 4 + 63) / 64), 64, 0, st, p);
+                else launch_k(h, kPdlTail, dec_av_kernel<NC, 8>, g4, 256, 0, st, p);
+            }
         } else {
             { ProfScope _ps(h, "dec_a", st); dec_a_kernel<NC><<<grid, 256, 0, st>>>(p); }
         }
@@ -830,7 +834,7 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         const bool b4 = NC == 5 && h->dec_impl != 0 && (W4 % 4 == 0) && (((uintptr_t)p.tin | (uintptr_t)p.comb) % 16 == 0);
         if (b4) {
             dim3 g4((W4 / 4 + 31) / 32, (H4 + 7) / 8, B);
-            { ProfScope _ps(h, "dec_b", st); launch_k(h, kPdlTail, dec_b4_kernel<NC, 2>, g4, 256, 0, st, p); }   // deeper unrolling is slower here, also at batch 1
+            if constexpr (NC == 5) { ProfScope _ps(h, "dec_b", st); launch_k(h, kPdlTail, dec_b4_kernel<NC, 2>, g4, 256, 0, st, p); }   // deeper unrolling is slower here, also at batch 1
         } else {
             ProfScope _ps(h, "dec_b", st); dec_b_kernel<NC><<<grid, 256, 0, st>>>(p);
         }
@@ -850,9 +854,11 @@ int run_tail(espnet_t* h, const espnet_forward_args* a, const Workspace& L, floa
         const bool vec_ok = NC == 5 && (W2 % 4 == 0) && (((uintptr_t)p.logits | (uintptr_t)p.prob_acc) % 16 == 0) && ((uintptr_t)p.mask % 8 == 0);
         if (vec_ok && h->dec_impl != 0) {
             dim3 g((W2 / 4 + 31) / 32, (H2 + 7) / 8, B);
-            { ProfScope _ps(h, "dec_c", st);
-              if (small_launch(h, (size_t)B * H2 * W2 / 4)) launch_k(h, kPdlLast, dec_c4_kernel<NC, 8>, g, 256, 0, st, p);
-              else launch_k(h, kPdlLast, dec_c4_kernel<NC, 2>, g, 256, 0, st, p); }
+            if constexpr (NC == 5) {
+                ProfScope _ps(h, "dec_c", st);
+                if (small_launch(h, (size_t)B * H2 * W2 / 4)) launch_k(h, kPdlLast, dec_c4_kernel<NC, 8>, g, 256, 0, st, p);
+                else launch_k(h, kPdlLast, dec_c4_kernel<NC, 2>, g, 256, 0, st, p);
+            }
         } else {
             dim3 g((W2 + 31) / 32, (H2 + 7) / 8, B);
             { ProfScope _ps(h, "dec_c", st); dec_c_kernel<NC><<<g, 256, 0, st>>>(p); }
