@@ -5,7 +5,9 @@
  * Nothing like this ABI exists in the reference (it is 100 % Python on top of PyTorch); each entry
  * point names the reference code it replaces (paths relative to the reference root).
  * Plain pointers and sizes only -- no torch types.  All device pointers are raw CUDA device
- * pointers owned by the caller; the library owns only its packed-weight buffer.  Every function
+ * pointers owned by the caller; the library owns only its packed-weight buffer (two exceptions, both opt-in and documented at
+ * their entry points: espnet_segment_host keeps grow-only device staging buffers and a private stream inside the handle,
+ * espnet_peer_alloc hands out device memory that espnet_peer_free releases).  Every function
  * returns 0 (ESPNET_OK) or a negative ESPNET_E* code; espnet_last_error() gives the message.
  * `stream` is a cudaStream_t passed as void* (NULL = default stream); all forward / stitch calls
  * are asynchronous on it.  There is no CPU and no cuDNN fallback anywhere behind this header.
@@ -132,7 +134,10 @@ ESPNET_API int espnet_set_profiling(espnet_t* h, int on);
 ESPNET_API int espnet_get_profile(espnet_t* h, char* names, float* total_ms, int* launches, int max_entries, int* n_entries);
 
 /* Host-buffer convenience (the call a reference user makes per crop, batched): pageable or pinned
- * HOST u8 BGR crops in, HOST u8 masks out; H2D, forward, D2H and the stream sync all inside. */
+ * HOST u8 BGR crops in, HOST u8 masks out; H2D, forward, D2H and the stream sync all inside.
+ * The ONE forward-path entry point that allocates: the handle keeps a device input buffer (B*H*W*3 bytes), a device mask buffer
+ * (B*H*W) and a workspace (espnet_workspace_bytes) of the largest shape seen so far (grow-only, freed by espnet_destroy) and runs
+ * on a private non-blocking stream.  Callers that manage device memory themselves use espnet_forward. */
 ESPNET_API int espnet_segment_host(espnet_t* h, const uint8_t* crops_host, int B, int H, int W,
                         const float mean[3], const float std_[3], uint8_t* masks_host);
 
